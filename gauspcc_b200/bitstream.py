@@ -1,0 +1,64 @@
+"""`xyz_pcc.bin` container (a-15) -- byte-identical layout to the reference.
+
+Reference: src/ai_pcc/GausPcgc/kit/op.py:32-48 (pack_byte_stream_ls / unpack_byte_stream) and the
+header written at src/gs_compress/HAC/utils/pcc_utils.py:198-203, parsed at :271-276:
+
+    f16 posQ | i32 n_base | i32[n_base,3] base xyz | u8[n_base] base occupancy
+    | u16 n_streams | n_streams x ( u32 len | bytes )
+
+Streams are level-major coarse->fine, stage-minor s0..s3 (pcc_utils.py:180-183).  Little-endian.
+"""
+from __future__ import annotations
+
+import struct
+from typing import List, Tuple
+
+import numpy as np
+
+
+def pack_byte_stream_ls(byte_stream_ls: List[bytes]) -> bytes:
+    if len(byte_stream_ls) > 0xFFFF:
+        raise ValueError("too many streams for the u16 count of the reference container")
+    parts = [struct.pack("<H", len(byte_stream_ls))]
+    for s in byte_stream_ls:
+        parts.append(struct.pack("<I", len(s)))
+        parts.append(bytes(s))
+    return b"".join(parts)
+
+
+def unpack_byte_stream(stream: bytes) -> List[bytes]:
+    (n,) = struct.unpack_from("<H", stream, 0)
+    out, cur = [], 2
+    for _ in range(n):
+        (ln,) = struct.unpack_from("<I", stream, cur)
+        if cur + 4 + ln > len(stream):
+            raise ValueError("truncated xyz_pcc.bin stream table")
+        out.append(stream[cur + 4:cur + 4 + ln])
+        cur += 4 + ln
+    return out
+
+
+def write_file(posQ: float, base_xyz: np.ndarray, base_occ: np.ndarray, streams: List[bytes]) -> bytes:
+    base_xyz = np.ascontiguousarray(base_xyz, dtype=np.int32).reshape(-1, 3)
+    base_occ = np.ascontiguousarray(base_occ, dtype=np.uint8).reshape(-1)
+    assert base_xyz.shape[0] == base_occ.shape[0]
+    return b"".join([
+        np.array(posQ, dtype=np.float16).tobytes(),
+        np.array(base_xyz.shape[0], dtype=np.int32).tobytes(),
+        base_xyz.tobytes(),
+        base_occ.tobytes(),
+        pack_byte_stream_ls(streams),
+    ])
+
+
+def read_file(blob: bytes) -> Tuple[np.float16, np.ndarray, np.ndarray, List[bytes]]:
+    if len(blob) < 6:
+        raise ValueError("truncated xyz_pcc.bin header")
+    posQ = np.frombuffer(blob[:2], dtype=np.float16)[0]
+    n0 = int(np.frombuffer(blob[2:6], dtype=np.int32)[0])
+    if n0 < 0 or 6 + 13 * n0 + 2 > len(blob):
+        raise ValueError("corrupt xyz_pcc.bin base section")
+    base_xyz = np.frombuffer(blob[6:6 + 12 * n0], dtype=np.int32).reshape(-1, 3)
+    base_occ = np.frombuffer(blob[6 + 12 * n0:6 + 13 * n0], dtype=np.uint8)
+    streams = unpack_byte_stream(blob[6 + 13 * n0:])
+    return posQ, base_xyz, base_occ, streams

@@ -1,0 +1,189 @@
+// kmap.cu -- coordinate hash table and kernel maps of the stride-1 K=5 submanifold conv.
+//
+// Replaces torchsparse 2.1.0's hash-map kernel-map build (selected by kmap_mode="hashmap",
+// src/gs_compress/HAC/utils/pcc_utils.py:50-52) for spnn.Conv3d(32,32,5)
+// (src/ai_pcc/GausPcgc/network_ue_4stage_conv.py:18-61).  The reference rebuilds the map for every
+// fresh SparseTensor (pcc_utils.py:100,108,124,132,140); here it is built ONCE per coordinate set and
+// shared by all convs on that set.
+//
+// Table: open addressing, linear probing, 16-byte slots {u64 key, u32 row, u32 pad} so a probe is one
+// 128-bit load; capacity = power of two >= 2n (the whole table of a 1M-row level is 32 MB: L2 resident).
+// Dense map is OFFSET-MAJOR [125][n] (coalesced over rows); offset index x-fastest
+// k = ((dz+2)*5 + (dy+2))*5 + (dx+2).  The conv consumes per-tile pair lists grouped by offset.
+#include "common.cuh"
+
+struct __align__(16) HashSlot { u64 key; u32 row; u32 pad; };
+
+__device__ __forceinline__ u32 hash_key(u64 k) {      // murmur3 fmix64
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (u32)k;
+}
+
+extern "C" int64_t gpc_hash_capacity(int64_t n) {
+    i64 cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    return cap;
+}
+
+__global__ void hash_insert_kernel(const u64 *__restrict__ keys, i64 n, HashSlot *table, u32 mask) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 key = keys[i];
+    u32 slot = hash_key(key) & mask;
+    while (true) {
+        unsigned long long prev = atomicCAS((unsigned long long *)&table[slot].key, (unsigned long long)GPC_EMPTY_KEY,
+                                            (unsigned long long)key);
+        if (prev == GPC_EMPTY_KEY || prev == key) { table[slot].row = (u32)i; return; }
+        slot = (slot + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ i32 hash_find(const HashSlot *__restrict__ table, u32 mask, u64 key) {
+    u32 slot = hash_key(key) & mask;
+    while (true) {
+        const uint4 raw = __ldg((const uint4 *)&table[slot]);
+        const u64 k = ((u64)raw.y << 32) | raw.x;
+        if (k == key) return (i32)raw.z;
+        if (k == GPC_EMPTY_KEY) return -1;
+        slot = (slot + 1) & mask;
+    }
+}
+
+extern "C" int gpc_hash_build(const uint64_t *keys, int64_t n, void *table, int64_t capacity, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    GPC_REQUIRE(capacity >= 2 * n && (capacity & (capacity - 1)) == 0, GPC_EINVAL, "capacity must be a power of two >= 2n");
+    GPC_CUDA_CHECK(cudaMemsetAsync(table, 0xFF, (size_t)capacity * sizeof(HashSlot), st));
+    if (n <= 0) return GPC_OK;
+    hash_insert_kernel<<<cdiv(n, 256), 256, 0, st>>>(keys, n, (HashSlot *)table, (u32)(capacity - 1));
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+__global__ void hash_lookup_kernel(const HashSlot *__restrict__ table, u32 mask, const u64 *__restrict__ q, i64 n,
+                                   i32 *__restrict__ rows) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rows[i] = hash_find(table, mask, q[i]);
+}
+extern "C" int gpc_hash_lookup(const void *table, int64_t capacity, const uint64_t *query, int64_t n, int32_t *rows,
+                               void *stream) {
+    if (n <= 0) return GPC_OK;
+    hash_lookup_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>((const HashSlot *)table, (u32)(capacity - 1), query, n, rows);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+// one thread per (offset k, row o); blockIdx.y = k so writes are coalesced over rows
+__global__ void kmap_dense_kernel(const HashSlot *__restrict__ table, u32 mask, const u64 *__restrict__ keys, i64 n,
+                                  i32 *__restrict__ map) {
+    const int k = blockIdx.y;
+    i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const int dx = k % 5 - 2, dy = (k / 5) % 5 - 2, dz = k / 25 - 2;
+    i32 r;
+    if (k == 62) r = (i32)o;
+    else {
+        const i64 delta = (i64)dx + ((i64)dy << 21) + ((i64)dz << 42);   // fields never under/overflow: |c| <= 2^20-16
+        r = hash_find(table, mask, (u64)((i64)keys[o] + delta));
+    }
+    map[(i64)k * n + o] = r;
+}
+extern "C" int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n, int32_t *map,
+                              void *stream) {
+    if (n <= 0) return GPC_OK;
+    dim3 grid(cdiv(n, 256), GPC_K3);
+    kmap_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>((const HashSlot *)table, (u32)(capacity - 1), keys, n, map);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+// ---------------------------------------------------------------- per-tile pair lists grouped by offset
+// counts[t*126 + k] = number of rows of tile t with a neighbour at offset k (k = 125 is a zero pad so
+// that the exclusive scan leaves seg[t*126+125] == start of tile t+1).
+constexpr int KP_THREADS = 256;
+
+__global__ void __launch_bounds__(KP_THREADS) kmap_pairs_count_kernel(const i32 *__restrict__ map, i64 n, int tile_rows,
+                                                                     u32 *__restrict__ counts) {
+    __shared__ u32 cnt[GPC_K3 + 1];
+    const i64 t = blockIdx.x;
+    const i64 r0 = t * tile_rows;
+    const int rows = (int)min((i64)tile_rows, n - r0);
+    for (int i = threadIdx.x; i <= GPC_K3; i += KP_THREADS) cnt[i] = 0;
+    __syncthreads();
+    for (int k = 0; k < GPC_K3; ++k) {
+        u32 c = 0;
+        for (int r = threadIdx.x; r < rows; r += KP_THREADS) c += map[(i64)k * n + r0 + r] >= 0;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= GPC_K3; i += KP_THREADS) counts[t * (GPC_K3 + 1) + i] = cnt[i];
+}
+
+__global__ void kmap_total_kernel(const u32 *__restrict__ seg, i64 m, u32 *__restrict__ n_pairs) { *n_pairs = seg[m]; }
+
+__global__ void __launch_bounds__(KP_THREADS) kmap_pairs_fill_kernel(const i32 *__restrict__ map, i64 n, int tile_rows,
+                                                                    const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr,
+                                                                    u16 *__restrict__ pair_row) {
+    __shared__ u32 warp_cnt[KP_THREADS / 32];
+    __shared__ u32 running;
+    const i64 t = blockIdx.x;
+    const i64 r0 = t * tile_rows;
+    const int rows = (int)min((i64)tile_rows, n - r0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < GPC_K3; ++k) {
+        const u32 seg_begin = seg[t * (GPC_K3 + 1) + k];
+        if (seg[t * (GPC_K3 + 1) + k + 1] == seg_begin) continue;          // block-uniform
+        if (threadIdx.x == 0) running = 0;
+        __syncthreads();
+        for (int rbase = 0; rbase < rows; rbase += KP_THREADS) {           // ascending row order inside a segment
+            const int r = rbase + threadIdx.x;
+            const i32 nb = r < rows ? map[(i64)k * n + r0 + r] : -1;
+            const u32 ballot = __ballot_sync(0xFFFFFFFFu, nb >= 0);
+            if (lane == 0) warp_cnt[warp] = __popc(ballot);
+            __syncthreads();
+            u32 before = running;
+            for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+            if (nb >= 0) {
+                const u32 p = seg_begin + before + __popc(ballot & ((1u << lane) - 1u));
+                pair_nbr[p] = (u32)nb;
+                pair_row[p] = (u16)r;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { u32 tot = 0; for (int w = 0; w < KP_THREADS / 32; ++w) tot += warp_cnt[w]; running += tot; }
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows) {
+    const i64 tiles = n > 0 ? (n + tile_rows - 1) / tile_rows : 1;
+    const i64 m = tiles * (GPC_K3 + 1);
+    return align_up((size_t)m * 4, 256) + align_up(scan_workspace_bytes<u32>(m), 256) + 1024;
+}
+extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, uint32_t *n_pairs,
+                                    void *ws, size_t ws_bytes, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    GPC_REQUIRE(tile_rows > 0 && tile_rows <= 65536, GPC_EINVAL, "tile_rows must be in 1..65536");
+    if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 4, st)); return GPC_OK; }
+    GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_pairs_workspace_bytes(n, tile_rows), GPC_ENOSPC, "workspace too small");
+    const i64 tiles = (n + tile_rows - 1) / tile_rows;
+    const i64 m = tiles * (GPC_K3 + 1);
+    u32 *counts = (u32 *)ws;
+    void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
+    kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, counts);
+    GPC_LAUNCH_CHECK();
+    PtrLoad<u32> pl{counts};
+    int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, seg, scan_ws, st);      // seg has m+1 entries
+    if (rc) return rc;
+    kmap_total_kernel<<<1, 1, 0, st>>>(seg, m, n_pairs);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr,
+                                   uint16_t *pair_row, void *stream) {
+    if (n <= 0) return GPC_OK;
+    const i64 tiles = (n + tile_rows - 1) / tile_rows;
+    kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, as_stream(stream)>>>(map, n, tile_rows, seg, pair_nbr, pair_row);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}

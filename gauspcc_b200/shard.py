@@ -1,0 +1,50 @@
+"""Multi-GPU: the path shards by scene.  One process per GPU, weights replicated
+(9.3 MB), scenes assigned by longest-processing-time-first, no collective inside the data path; one
+small all_gather of per-scene results {n_points, file_bytes, t_enc_us, t_dec_us} at the end.
+
+The reference has no distributed code at all (every script pins one GPU, e.g.
+scripts/gs_compress/run_ours_hac.sh:7); this module is the B200-box equivalent of running its
+per-scene loop on 8 GPUs.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def assign_scenes(sizes: Sequence[int], world_size: int) -> List[List[int]]:
+    """Greedy LPT: scenes sorted by size descending, each to the currently lightest rank.
+    Deterministic (ties by scene index), identical on every rank without communication."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world_size
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += int(sizes[i])
+    return out
+
+
+def gather_results(local: torch.Tensor, n_scenes: int, assignment: List[List[int]]) -> torch.Tensor:
+    """local: int64 [len(assignment[rank]), F] on this rank's device -> int64 [n_scenes, F] on every rank.
+    Ragged shards are padded to the longest one so a single all_gather_into_tensor suffices."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    F = local.shape[1]
+    longest = max(len(a) for a in assignment) if assignment else 0
+    pad = torch.zeros((longest, F), dtype=torch.int64, device=local.device)
+    pad[: local.shape[0]] = local
+    if world > 1:
+        allr = torch.empty((world * longest, F), dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(allr, pad)
+    else:
+        allr = pad
+    out = torch.zeros((n_scenes, F), dtype=torch.int64, device=local.device)
+    for r in range(world):
+        idx = assignment[r]
+        if idx:
+            out[torch.tensor(idx, device=local.device)] = allr[r * longest: r * longest + len(idx)]
+    assert len(assignment[rank]) == local.shape[0]
+    return out

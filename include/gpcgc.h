@@ -1,0 +1,159 @@
+/*
+ * gpcgc.h -- C ABI of libgpcgc.so: the B200 (sm_100a) implementation of the GausPcgc
+ * anchor-geometry codec hot path of Wangkkklll/GausPcc.
+ *
+ * Boundary replaced (reference file:line, relative to /root/reference):
+ *   src/gs_compress/HAC/utils/pcc_utils.py:12-22    calculate_morton_order
+ *   src/gs_compress/HAC/utils/pcc_utils.py:24-217   compress_point_cloud
+ *   src/gs_compress/HAC/utils/pcc_utils.py:230-400  decompress_point_cloud
+ * and, underneath them, the third-party calls those functions make
+ *   torchsparse 2.1.0: SparseTensor / spnn.Conv3d / hash kernel maps
+ *                      (kit/nn.py:14-16,31; network_ue_4stage_conv.py:18-61)
+ *   torch:             sort x4 (kit/op.py:17-30), embedding / linear / softmax / cumsum
+ *   torchac 0.9.3:     encode/decode_int16_normalized_cdf (pcc_utils.py:174-177,322-366)
+ *
+ * Conventions
+ *   - every entry point is extern "C", returns 0 on success or a negative GPC_E* code;
+ *     gpc_last_error() gives a thread-local message.
+ *   - pointers are DEVICE pointers unless the name ends in _h (host).  No allocation happens
+ *     inside the library: the caller provides outputs and workspaces (sizes from the
+ *     *_workspace_bytes queries).  `stream` is a cudaStream_t passed as void*.
+ *   - a voxel key is u64: (z+2^20)<<42 | (y+2^20)<<21 | (x+2^20); ascending key order is the
+ *     reference's row order: lexicographic (z,y,x) = op.sort_CF = calculate_morton_order.
+ *     Valid coordinates: |c| <= GPC_COORD_MAX.
+ *   - feature rows are fp32 [n, 32] row-major (128 B per row), GPC_C == 32, K == 5 (K^3 == 125)
+ *     as in the reference call sites (pcc_utils.py:28-29).
+ */
+#ifndef GPCGC_H
+#define GPCGC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPC_C 32
+#define GPC_K 5
+#define GPC_K3 125
+#define GPC_COORD_BIAS (1 << 20)
+#define GPC_COORD_MAX ((1 << 20) - 16)
+
+#define GPC_OK 0
+#define GPC_EINVAL (-1)     /* bad argument */
+#define GPC_ECUDA (-2)      /* CUDA runtime error (see gpc_last_error) */
+#define GPC_ERANGE (-3)     /* coordinate outside +-GPC_COORD_MAX or not integral */
+#define GPC_ENOSPC (-4)     /* workspace / output too small */
+#define GPC_EDATA (-5)      /* corrupt bitstream / symbol out of range */
+
+const char *gpc_last_error(void);
+int gpc_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t gpc_launch_count(void);
+
+/* key transform for sorting: compact = ((z-minz)<<sz) | ((y-miny)<<sy) | (x-minx) on the biased
+ * 21-bit fields; digits of `compact` are what the radix sort consumes (fewer passes than 63 bits) */
+typedef struct { uint32_t minx, miny, minz, sy, sz, total_bits; } gpc_key_xform;
+
+/* ---- a-1/a-2: voxel keys and ordering (pcc_utils.py:12-22; HAC/scene/gaussian_model.py:1107) ---- */
+/* xyz [n,3] row-major -> keys[n]; *status (device int32, caller-zeroed) gets bit0 set on a
+ * non-integral value, bit1 on out-of-range. */
+int gpc_pack_keys_f32(const float *xyz, int64_t n, uint64_t *keys, int32_t *status, void *stream);
+int gpc_pack_keys_i32(const int32_t *xyz, int64_t n, uint64_t *keys, int32_t *status, void *stream);
+int gpc_unpack_keys_i32(const uint64_t *keys, int64_t n, int32_t *xyz, void *stream);
+int gpc_unpack_keys_f32(const uint64_t *keys, int64_t n, float scale, float *xyz, void *stream);
+/* min/max of the three biased fields -> minmax[6] = {minx,miny,minz,maxx,maxy,maxz} (device u32) */
+int gpc_key_minmax(const uint64_t *keys, int64_t n, uint32_t *minmax, void *stream);
+/* host helper: builds the transform from minmax read back by the caller */
+int gpc_make_xform_h(const uint32_t *minmax_h, gpc_key_xform *out_h);
+
+size_t gpc_sort_workspace_bytes(int64_t n);
+/* stable LSD radix sort of (key, val) by compact(key); vals_in == NULL means val = row index.
+ * keys_in/vals_in are clobbered; result in keys_out/vals_out (keys_out may be NULL). */
+int gpc_sort_pairs(uint64_t *keys_in, uint32_t *vals_in, uint64_t *keys_out, uint32_t *vals_out,
+                   int64_t n, gpc_key_xform xf, void *ws, size_t ws_bytes, void *stream);
+/* calculate_morton_order: permutation (int64) that sorts rows by (z,y,x), stable.
+ * is_f32 != 0: xyz is float32, else int32.  Synchronises the stream (it reads min/max back). */
+size_t gpc_lexorder_workspace_bytes(int64_t n);
+int gpc_lexorder_zyx(const void *xyz, int is_f32, int64_t n, int64_t *out_idx,
+                     void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a-4: pyramid down (FOG, kit/nn.py:38-55) ---- */
+size_t gpc_pyramid_workspace_bytes(int64_t n);
+/* keys sorted ascending (duplicates allowed) -> unique keys; *n_out is a device u32 */
+int gpc_unique_sorted(const uint64_t *keys, int64_t n, uint64_t *out_keys, uint32_t *n_out,
+                      void *ws, size_t ws_bytes, void *stream);
+/* child keys (sorted, unique) -> parent keys (sorted, unique) + occupancy byte; xf = transform
+ * covering the PARENT level's extent; *n_parent device u32 */
+int gpc_pyramid_down(const uint64_t *child_keys, int64_t n_child, gpc_key_xform parent_xf,
+                     uint64_t *parent_keys, uint8_t *parent_occ, uint32_t *n_parent,
+                     void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a-8: expand children (FCG, kit/nn.py:77-98 + sort_CF) ---- */
+size_t gpc_expand_workspace_bytes(int64_t n_parent);
+/* parents sorted -> children emitted directly in (z,y,x) order (no sort): child_keys[n_child],
+ * child_parent[n_child] = parent row.  n_child must equal sum(popcount(occ)). */
+int gpc_expand_children(const uint64_t *parent_keys, const uint8_t *parent_occ, int64_t n_parent,
+                        int64_t n_child, uint64_t *child_keys, uint32_t *child_parent,
+                        void *ws, size_t ws_bytes, void *stream);
+/* decode epilogue (pcc_utils.py:375-379): children in PARENT-MAJOR order (octant ascending), as
+ * float32 xyz * scale -- the row order the reference returns. */
+int gpc_expand_leaves_f32(const uint64_t *parent_keys, const uint8_t *parent_occ, int64_t n_parent,
+                          int64_t n_child, float scale, float *xyz, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- kernel maps (torchsparse hashmap kmap; pcc_utils.py:50-52) ---- */
+int64_t gpc_hash_capacity(int64_t n);                      /* slots; table bytes = 16 * slots */
+int gpc_hash_build(const uint64_t *keys, int64_t n, void *table, int64_t capacity, void *stream);
+int gpc_hash_lookup(const void *table, int64_t capacity, const uint64_t *query, int64_t n,
+                    int32_t *rows, void *stream);
+/* dense map, OFFSET-MAJOR: map[k*n + o] = row of (c_o + d_k) or -1; k = ((dz+2)*5+(dy+2))*5+(dx+2) */
+int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n,
+                   int32_t *map, void *stream);
+/* tile pair lists for the conv: tiles of `tile_rows` consecutive output rows; for tile t and offset
+ * k the pairs are [seg[t*126+k], seg[t*126+k+1]) (seg[t*126+125] == next tile's start);
+ * pair_nbr = input row, pair_row = output row - t*tile_rows.  Two calls: count (fills seg as an
+ * exclusive scan, *n_pairs device u32), then fill. */
+size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows);
+int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, uint32_t *n_pairs,
+                         void *ws, size_t ws_bytes, void *stream);
+int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg,
+                        uint32_t *pair_nbr, uint16_t *pair_row, void *stream);
+
+/* ---- a-7/a-10/a-12: sparse conv (spnn.Conv3d(32,32,5), bias-less) ---- */
+/* y[o,:] = act( sum_k x[nbr_k(o),:] . W[k] (+ residual[o,:]) ); W [125,32,32] fp32;
+ * offsets accumulate in ascending k for every row (deterministic). flags: bit0 = ReLU. */
+#define GPC_CONV_RELU 1
+int gpc_spconv_fwd(const float *x, const float *W, const uint32_t *seg, const uint32_t *pair_nbr,
+                   const uint16_t *pair_row, int64_t n, int tile_rows, const float *residual,
+                   int flags, float *y, void *stream);
+
+/* ---- a-6/a-9/a-12: embeddings ---- */
+/* out[o,:] = table[idx[o],:]  (prior_embedding, network_ue_4stage_conv.py:15) */
+int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *stream);
+/* out[j,:] = feat[parent[j],:] + temb[octant(child_key[j]),:]  (FCG replicate + TargetEmbedding) */
+int gpc_gather_parent_add_octant(const float *feat, const uint32_t *parent, const uint64_t *child_keys,
+                                 int64_t n_child, const float *temb, float *out, void *stream);
+/* out[o,:] = u[o,:] + emb[occ[o] >> shift, :]   (pred_head_s{1,2,3}_emb; shift = 7, 6, 4) */
+int gpc_add_ctx_embed(const float *u, const uint8_t *occ, int shift, const float *emb, int64_t n,
+                      float *out, void *stream);
+
+/* ---- a-12/a-13: fused head: Linear-ReLU-Linear-softmax-cumsum-quantise ---- */
+/* cdf [n, A+1] uint16 (int16 bit pattern of kit/op.py:67-79); prob [n, A] optional (may be NULL) */
+int gpc_head_cdf(const float *f, int64_t n, const float *W1, const float *b1, const float *W2,
+                 const float *b2, int A, uint16_t *cdf, float *prob, void *stream);
+/* a-11: symbol of stage i from the occupancy byte: sym = (occ >> shift) & mask */
+int gpc_split_symbol(const uint8_t *occ, int64_t n, int shift, int mask, uint8_t *sym, void *stream);
+/* decode: occ[o] |= sym[o] << shift */
+int gpc_merge_symbol(uint8_t *occ, int64_t n, int shift, const uint8_t *sym, void *stream);
+
+/* ---- a-14: host range coder (torchac-compatible) ---- */
+int gpc_ac_encode_h(const uint16_t *cdf_h, const uint8_t *sym_h, int64_t n, int Lp,
+                    uint8_t *out_h, int64_t cap, int64_t *out_len_h);
+int gpc_ac_decode_h(const uint16_t *cdf_h, const uint8_t *in_h, int64_t in_len, int64_t n, int Lp,
+                    uint8_t *sym_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPCGC_H */

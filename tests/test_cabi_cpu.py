@@ -1,0 +1,159 @@
+"""CPU-side checks of the product package: the C-ABI library loads and exports every symbol declared in
+include/gpcgc.h, the host range coder and the container are bit-exact against the oracle / golden
+vectors, and the product fails loudly without a GPU (no fallback).  No device compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from gauspcc_b200 import _lib, bitstream
+from gauspcc_b200 import weights as W
+from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "gpcgc.h")).read()
+    declared = set(re.findall(r"\b(gpc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gpcgc.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gpc_version() >= 1
+
+
+def _enc(lib, cdf, sym):
+    n, Lp = cdf.shape
+    out = np.empty(4 * n + 64, dtype=np.uint8)
+    ln = C.c_int64(0)
+    rc = lib.gpc_ac_encode_h(cdf.ctypes.data_as(C.c_void_p), sym.ctypes.data_as(C.c_void_p), n, Lp,
+                             out.ctypes.data_as(C.c_void_p), out.size, C.byref(ln))
+    assert rc == 0
+    return out[:ln.value].tobytes()
+
+
+def _dec(lib, cdf, stream):
+    n, Lp = cdf.shape
+    buf = np.frombuffer(stream, dtype=np.uint8).copy() if stream else np.zeros(1, np.uint8)
+    sym = np.empty(n, dtype=np.uint8)
+    assert lib.gpc_ac_decode_h(cdf.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p), len(stream), n, Lp,
+                               sym.ctypes.data_as(C.c_void_p)) == 0
+    return sym
+
+
+def test_host_range_coder_known_answers():
+    lib = _lib.load()
+    cdf = np.tile(np.array([[0, 32768, 0]], dtype=np.uint16), (8, 1))
+    assert _enc(lib, cdf, np.array([0, 1, 1, 0, 1, 0, 0, 1], np.uint8)).hex() == "6940"
+    q = np.tile(np.array([[0, 45873, 52428, 58982, 0]], dtype=np.uint16), (6, 1))
+    assert _enc(lib, q, np.array([0, 0, 3, 0, 1, 2], np.uint8)).hex() == "77c0"
+    q = np.array([[*(4096 * np.arange(16)), 0]], dtype=np.uint16)
+    assert _enc(lib, q, np.array([15], np.uint8)).hex() == "f4"
+
+
+@pytest.mark.parametrize("A", [2, 4, 16])
+@pytest.mark.parametrize("n", [0, 1, 7, 5000])
+def test_host_range_coder_matches_oracle(A, n):
+    lib = _lib.load()
+    rng = np.random.default_rng(A * 1000 + n)
+    conc = rng.choice([0.05, 1.0, 20.0])
+    p = rng.dirichlet(np.full(A, conc), size=max(n, 1)).astype(np.float32)[:n]
+    if n > 10:
+        p[:3] = 0; p[:3, A - 1] = 1.0            # degenerate rows: p = 1 on the last symbol
+        p[3:6] = 0; p[3:6, 0] = 1.0
+    cdf = O.cdf_u16(p) if n else np.zeros((0, A + 1), np.uint16)
+    # symbols drawn from p, plus some improbable ones (long carry chains / pending bits)
+    sym = np.array([rng.choice(A, p=row / row.sum()) for row in p.astype(np.float64)], dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    if n > 100:
+        sym[50:60] = rng.integers(0, A, 10)
+    ref = O.ac_encode(cdf, sym.astype(np.int16)) if n else O.ac_encode(np.zeros((0, A + 1), np.uint16), np.zeros(0, np.int16))
+    got = _enc(lib, np.ascontiguousarray(cdf), sym)
+    assert got == ref
+    assert np.array_equal(_dec(lib, cdf, got), sym)
+    assert np.array_equal(O.ac_decode(cdf, got).astype(np.uint8), sym)
+
+
+def test_host_range_coder_rejects_bad_symbol():
+    lib = _lib.load()
+    cdf = np.array([[0, 100, 0]], dtype=np.uint16)
+    out = np.empty(64, np.uint8)
+    ln = C.c_int64(0)
+    rc = lib.gpc_ac_encode_h(cdf.ctypes.data_as(C.c_void_p), np.array([2], np.uint8).ctypes.data_as(C.c_void_p), 1, 3,
+                             out.ctypes.data_as(C.c_void_p), 64, C.byref(ln))
+    assert rc == -5 and b"out of range" in lib.gpc_last_error()
+
+
+def test_container_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "op_golden.npz"))
+    packed = g["packed"].tobytes()
+    parts = bitstream.unpack_byte_stream(packed)
+    assert [len(p) for p in parts] == list(g["stream_lens"])
+    assert bitstream.pack_byte_stream_ls(parts) == packed
+    assert bitstream.pack_byte_stream_ls([b"\x01\x02", b"", b"\xff"]).hex() == "03000200000001020000000001000000ff"
+
+
+def test_file_layout_matches_reference_driver(golden_dir):
+    cg = np.load(os.path.join(golden_dir, "codec_golden.npz"))
+    blob = cg["hac600_bin"].tobytes()
+    posQ, bx, bo, streams = bitstream.read_file(blob)
+    assert float(posQ) == 1.0 and bx.shape[0] == bo.shape[0] < 64 and len(streams) % 4 == 0
+    assert bitstream.write_file(1, bx, bo, streams) == blob
+    with pytest.raises(ValueError):
+        bitstream.read_file(blob[:20])
+
+
+def test_make_xform_host():
+    lib = _lib.load()
+    mm = np.array([10, 20, 30, 10 + 255, 20 + 256, 30], dtype=np.uint32)
+    xf = _lib.KeyXform()
+    assert lib.gpc_make_xform_h(mm.ctypes.data_as(C.c_void_p), C.byref(xf)) == 0
+    assert (xf.minx, xf.miny, xf.minz, xf.sy, xf.sz, xf.total_bits) == (10, 20, 30, 8, 17, 17)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gauspcc_b200 import pcc_utils
+    with pytest.raises(_lib.GpcError):
+        pcc_utils.calculate_morton_order(torch.zeros(4, 3))
+    with pytest.raises(AssertionError):
+        pcc_utils.calculate_morton_order(torch.zeros(4, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gauspcc_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "gpcgc_oracle" not in src, f
+
+
+def test_weights_layout_and_validation():
+    sd = W.make_synthetic_state_dict()
+    lay = W.reference_layout()
+    assert list(sd) == list(lay) and sum(v.numel() for v in sd.values()) == 2318176   # 18*125*32*32 + embeddings + heads + fog
+    W.validate_state_dict(sd)
+    bad = dict(sd); bad.pop("pred_head_s2_emb.weight")
+    with pytest.raises(RuntimeError):
+        W.validate_state_dict(bad)
+    bad = dict(sd); bad["prior_embedding.weight"] = torch.zeros(255, 32)
+    with pytest.raises(RuntimeError):
+        W.validate_state_dict(bad)
+    assert torch.equal(W.make_synthetic_state_dict()["spatial_conv_s3.2.kernel"], sd["spatial_conv_s3.2.kernel"])
+
+
+def test_synthetic_clouds():
+    a = hac_like_cloud(20000, 0)
+    assert a.shape == (20000, 3) and a.dtype == np.int32 and np.unique(a, axis=0).shape[0] == 20000
+    assert a.min() < 0 < a.max() and np.abs(a).max() < (1 << 20) - 16
+    assert np.array_equal(a, hac_like_cloud(20000, 0)) and not np.array_equal(a, hac_like_cloud(20000, 1))
+    b = uniform_unique_cloud(5000, 1, extent_log2=10)
+    assert np.unique(b, axis=0).shape[0] == 5000

@@ -1,0 +1,369 @@
+"""GPU parity tests: every stage of the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs, the committed golden fixtures, and size-independent properties at full size.
+
+Bars (BASELINE.json north_star): bit-exact order / kernel maps / pyramid / decoded geometry;
+probabilities within 1e-3 abs; total bitstream bytes within 0.5 %."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3          # north_star: occupancy probabilities within 1e-3 absolute
+SIZE_TOL = 0.005         # north_star: total geometry bitstream size within 0.5 %
+
+
+@pytest.fixture(scope="module")
+def env(weights_np):
+    from gauspcc_b200 import _lib
+    from gauspcc_b200.codec import DeviceWeights, GausPcgcCodec
+    from gauspcc_b200.weights import make_synthetic_state_dict
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    sd = make_synthetic_state_dict()
+    codec = GausPcgcCodec(DeviceWeights(sd, dev), dev)
+    return {"lib": _lib.load(), "codec": codec, "dev": dev, "sd": sd, "w": weights_np}
+
+
+def _keys_of(codec, xyz_np):
+    t = torch.tensor(np.ascontiguousarray(xyz_np, dtype=np.int32), device=codec.dev)
+    keys, meta = codec.pack_keys(t)
+    return keys, meta.cpu().numpy()
+
+
+def _unpack(codec, keys):
+    from gauspcc_b200.codec import _ptr
+    out = torch.empty((keys.shape[0], 3), dtype=torch.int32, device=codec.dev)
+    codec._call("gpc_unpack_keys_i32", _ptr(keys), keys.shape[0], _ptr(out), codec._stream())
+    return out.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- a-2 calculate_morton_order
+@pytest.mark.parametrize("n,lo,hi,dtype", [(1, -5, 5, torch.float32), (2, 0, 2, torch.float32), (1000, -300, 300, torch.float32),
+                                           (50000, -20000, 20000, torch.float32), (50000, 0, 40, torch.int32),
+                                           (4097, -1000000, 1000000, torch.int32), (300000, -30000, 30000, torch.float32)])
+def test_calculate_morton_order(env, n, lo, hi, dtype):
+    from gauspcc_b200.pcc_utils import calculate_morton_order
+    from oracle import oracle as O
+    rng = np.random.default_rng(n)
+    xyz = rng.integers(lo, hi, size=(n, 3))
+    x = torch.tensor(xyz, dtype=dtype, device=env["dev"])
+    got = calculate_morton_order(x)
+    assert got.dtype == torch.int64 and got.device == x.device and got.shape == (n,)
+    assert np.array_equal(got.cpu().numpy(), O.lexorder(xyz))          # duplicates included: stable
+    cpu = calculate_morton_order(torch.tensor(xyz, dtype=dtype))       # CPU tensor in -> CPU tensor out
+    assert cpu.device.type == "cpu" and np.array_equal(cpu.numpy(), got.cpu().numpy())
+
+
+def test_calculate_morton_order_golden(env, golden_dir):
+    from gauspcc_b200.pcc_utils import calculate_morton_order
+    g = np.load(os.path.join(golden_dir, "op_golden.npz"))
+    for i in range(3):
+        x = torch.tensor(g[f"mo_in{i}"], device=env["dev"])
+        assert np.array_equal(calculate_morton_order(x).cpu().numpy(), g[f"mo_out{i}"])   # reference's own output
+    with pytest.raises(AssertionError):
+        calculate_morton_order(torch.zeros(5, 2, device=env["dev"]))
+    assert calculate_morton_order(torch.zeros(0, 3, device=env["dev"])).shape == (0,)
+
+
+def test_morton_order_full_size_properties(env):
+    from gauspcc_b200.pcc_utils import calculate_morton_order
+    from gauspcc_b200.synth import hac_like_cloud
+    xyz = hac_like_cloud(1_000_000, 0)
+    x = torch.tensor(xyz, dtype=torch.float32, device=env["dev"])
+    idx = calculate_morton_order(x)
+    s = x[idx].to(torch.int64)
+    key = (s[:, 2] + (1 << 20)) * (1 << 42) + (s[:, 1] + (1 << 20)) * (1 << 21) + (s[:, 0] + (1 << 20))
+    assert bool((key[1:] > key[:-1]).all())                                            # sorted, unique cloud
+    assert torch.equal(torch.sort(idx)[0], torch.arange(x.shape[0], device=env["dev"]))  # a permutation
+    assert torch.equal(calculate_morton_order(x[idx]), torch.arange(x.shape[0], device=env["dev"]))  # idempotent
+
+
+# ----------------------------------------------------------------------------- keys / sort / unique
+def test_pack_unpack_and_status(env):
+    codec = env["codec"]
+    rng = np.random.default_rng(1)
+    xyz = rng.integers(-(1 << 20) + 16, (1 << 20) - 16, size=(10000, 3)).astype(np.int32)
+    keys, meta = _keys_of(codec, xyz)
+    assert meta[0] == 0
+    assert np.array_equal(_unpack(codec, keys), xyz)
+    b = 1 << 20
+    assert list(meta[2:8]) == list(xyz.min(0) + b) + list(xyz.max(0) + b)
+    k64 = keys.cpu().numpy().astype(np.uint64)
+    ref = ((xyz[:, 2].astype(np.int64) + b) << 42) | ((xyz[:, 1].astype(np.int64) + b) << 21) | (xyz[:, 0].astype(np.int64) + b)
+    assert np.array_equal(k64, ref.astype(np.uint64))
+    _, meta = codec.pack_keys(torch.tensor([[0.5, 1, 2]], dtype=torch.float32, device=codec.dev))
+    assert meta.cpu().numpy()[0] & 1
+    _, meta = codec.pack_keys(torch.tensor([[1 << 20, 1, 2]], dtype=torch.int32, device=codec.dev))
+    assert meta.cpu().numpy()[0] & 2
+
+
+def test_sort_unique(env):
+    codec = env["codec"]
+    rng = np.random.default_rng(2)
+    xyz = rng.integers(-50, 50, size=(200000, 3)).astype(np.int32)       # many duplicates
+    keys, meta = _keys_of(codec, xyz)
+    leaf = codec.sort_unique(keys, meta[2:8].astype(np.uint32))
+    ref = np.unique(xyz, axis=0)
+    ref = ref[np.lexsort((ref[:, 0], ref[:, 1], ref[:, 2]))]
+    assert np.array_equal(_unpack(codec, leaf), ref)
+
+
+# ----------------------------------------------------------------------------- a-4 / a-8 pyramid
+@pytest.mark.parametrize("n,seed,ext", [(5000, 0, 16), (60000, 1, 16), (3000, 2, 8), (40, 3, 6), (1, 4, 6)])
+def test_pyramid_down_and_expand(env, n, seed, ext):
+    from gauspcc_b200.synth import hac_like_cloud
+    from oracle import oracle as O
+    codec = env["codec"]
+    xyz = hac_like_cloud(n, seed, extent_log2=ext) if n > 1 else np.array([[-7, 3, 900]], dtype=np.int32)
+    ref_levels = O.build_pyramid(xyz)
+    keys, meta = _keys_of(codec, xyz)
+    leaf = codec.sort_unique(keys, meta[2:8].astype(np.uint32))
+    levels = codec.build_pyramid(leaf, meta[2:8].astype(np.int64))
+    assert [l.n for l in levels] == [c.shape[0] for c, _ in ref_levels]
+    for lv, (rc, ro) in zip(levels, ref_levels):
+        assert np.array_equal(_unpack(codec, lv.keys), rc)
+        assert np.array_equal(lv.occ.cpu().numpy(), ro)
+    # expansion (FCG + sort_CF) without a sort: children keys and parent rows, bit-exact
+    for d, lv in enumerate(levels):
+        cc, par = O.fcg(*ref_levels[d])
+        ck, cp = codec.expand(lv, cc.shape[0])
+        assert np.array_equal(_unpack(codec, ck), cc)
+        assert np.array_equal(cp.cpu().numpy().astype(np.int64), par)
+        if d + 1 < len(levels):
+            assert torch.equal(ck, levels[d + 1].keys)
+
+
+# ----------------------------------------------------------------------------- kernel maps
+@pytest.mark.parametrize("n,seed,ext", [(3000, 0, 7), (40000, 1, 16), (50, 2, 3), (1, 3, 3)])
+def test_kernel_map(env, n, seed, ext):
+    from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
+    from oracle import oracle as O
+    codec = env["codec"]
+    xyz = uniform_unique_cloud(n, seed, extent_log2=ext) if ext < 10 else hac_like_cloud(n, seed, extent_log2=ext)
+    xyz = xyz[O.sort_zyx_perm(xyz)]
+    keys, _ = _keys_of(codec, xyz)
+    km, dense = codec.build_kmap(keys, keep_dense=True)
+    ref = O.kmap(xyz, 5)
+    assert np.array_equal(dense.cpu().numpy().T, ref)                   # dense map, canonical indexing
+    # pair lists: segment (tile, k) lists exactly the rows with a neighbour at k, ascending
+    seg = km.seg.cpu().numpy().astype(np.int64)
+    nbr = km.pair_nbr.cpu().numpy()
+    row = km.pair_row.cpu().numpy().astype(np.int64) & 0xFFFF
+    assert km.n_pairs == int((ref >= 0).sum()) == seg[-1]
+    tr = km.tile_rows
+    for t in range((n + tr - 1) // tr):
+        sub = ref[t * tr:(t + 1) * tr]
+        for k in (0, 31, 62, 63, 124):
+            rr = np.nonzero(sub[:, k] >= 0)[0]
+            a, b = seg[t * 126 + k], seg[t * 126 + k + 1]
+            assert np.array_equal(row[a:b], rr) and np.array_equal(nbr[a:b], sub[rr, k])
+
+
+def test_hash_lookup_misses(env):
+    from gauspcc_b200.codec import _ptr
+    codec = env["codec"]
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [-5, 7, 9]], dtype=np.int32)
+    keys, _ = _keys_of(codec, xyz)
+    cap = codec.lib.gpc_hash_capacity(3)
+    table = codec._ws(cap * 16)
+    codec._call("gpc_hash_build", _ptr(keys), 3, _ptr(table), cap, codec._stream())
+    q, _ = _keys_of(codec, np.array([[1, 0, 0], [2, 0, 0], [-5, 7, 9], [0, 0, 1]], dtype=np.int32))
+    rows = torch.empty(4, dtype=torch.int32, device=codec.dev)
+    codec._call("gpc_hash_lookup", _ptr(table), cap, _ptr(q), 4, _ptr(rows), codec._stream())
+    assert rows.cpu().tolist() == [1, -1, 2, -1]
+
+
+# ----------------------------------------------------------------------------- sparse conv / head
+@pytest.mark.parametrize("n,ext", [(2000, 6), (30000, 16), (700, 4)])
+def test_sparse_conv(env, n, ext):
+    from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
+    from oracle import oracle as O
+    codec, w = env["codec"], env["w"]
+    xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
+    xyz = xyz[O.sort_zyx_perm(xyz)]
+    keys, _ = _keys_of(codec, xyz)
+    km = codec.build_kmap(keys)
+    ref_km = O.kmap(xyz, 5)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(n, 32)).astype(np.float32)
+    res = rng.normal(size=(n, 32)).astype(np.float32)
+    xd, rd = torch.tensor(x, device=codec.dev), torch.tensor(res, device=codec.dev)
+    Wk = w["target_resnet.2.conv1.kernel"]
+    y = codec.conv(xd, 7, km).cpu().numpy()
+    ref = O.conv(x, Wk, ref_km)
+    scale = np.abs(ref).max()
+    assert np.abs(y - ref).max() <= 2e-5 * max(scale, 1.0)
+    y2 = codec.conv(xd, 7, km, residual=rd, relu=True).cpu().numpy()
+    assert np.abs(y2 - np.maximum(ref + res, 0)).max() <= 2e-5 * max(scale, 1.0)
+    # deterministic: bit-identical on a second launch (encoder/decoder CDF identity depends on it)
+    assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)
+    # linearity in x
+    y3 = codec.conv(2 * xd, 7, km).cpu().numpy()
+    assert np.allclose(y3, 2 * y, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("i", [0, 1, 2, 3])
+def test_head_cdf(env, i):
+    from gauspcc_b200.codec import _ptr
+    from oracle import oracle as O
+    codec, w = env["codec"], env["w"]
+    A = (2, 2, 4, 16)[i]
+    rng = np.random.default_rng(i)
+    n = 5003
+    f = (rng.normal(size=(n, 32)) * 3).astype(np.float32)
+    f[:4] = 0
+    f[4:8] = 1e4                     # saturating logits
+    fd = torch.tensor(f, device=codec.dev)
+    cdf = torch.empty((n, A + 1), dtype=torch.int16, device=codec.dev)
+    prob = torch.empty((n, A), dtype=torch.float32, device=codec.dev)
+    w1, b1, w2, b2 = codec.w.head[i]
+    codec._call("gpc_head_cdf", _ptr(fd), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), A, _ptr(cdf), _ptr(prob), codec._stream())
+    ref_p = O.head(f, w[f"pred_head_s{i}.0.weight"], w[f"pred_head_s{i}.0.bias"], w[f"pred_head_s{i}.2.weight"],
+                   w[f"pred_head_s{i}.2.bias"])
+    got_p = prob.cpu().numpy()
+    assert np.abs(got_p - ref_p).max() < 1e-5
+    got_c = cdf.cpu().numpy().view(np.uint16).astype(np.int64)
+    # exact quantisation rule on the kernel's own probabilities (kit/op.py:67-79) ...
+    assert np.array_equal(got_c, O.cdf_u16(got_p).astype(np.int64))
+    # ... and within one step of the oracle's end-to-end CDF
+    ref_c = O.cdf_u16(ref_p).astype(np.int64)
+    assert np.abs(got_c[:, :-1] - ref_c[:, :-1]).max() <= 1
+    assert (got_c[:, 0] == 0).all() and (np.diff(got_c[:, :-1], axis=1) >= 1).all()      # strictly increasing rows
+
+
+# ----------------------------------------------------------------------------- full codec
+def _encode_file(codec, xyz_t):
+    from gauspcc_b200 import bitstream
+    bx, bo, streams, aux = codec.encode(xyz_t, collect=True)
+    return bitstream.write_file(1, bx, bo, streams), (bx, bo, streams), aux
+
+
+@pytest.mark.parametrize("n,seed,ext", [(3000, 0, 16), (20000, 1, 16), (2500, 5, 12), (900, 7, 5)])
+def test_codec_vs_oracle(env, n, seed, ext):
+    from gauspcc_b200.synth import hac_like_cloud
+    from oracle import oracle as O
+    codec, w = env["codec"], env["w"]
+    xyz = hac_like_cloud(n, seed, extent_log2=ext)
+    x = torch.tensor(xyz, dtype=torch.float32, device=codec.dev)
+    blob, (bx, bo, streams), aux = _encode_file(codec, x)
+    ref_blob, ref = O.encode(xyz, w, collect=True)
+    # pyramid / base / stream structure bit-exact
+    assert np.array_equal(bx, ref["levels"][0][0]) and np.array_equal(bo, ref["levels"][0][1])
+    assert len(streams) == 4 * len(ref["aux"])
+    for ck, lv in zip(aux["child_keys"], ref["aux"]):
+        assert np.array_equal(_unpack(codec, ck), lv["coords"])
+    # probabilities of every (level, stage)
+    k = 0
+    worst = 0.0
+    for lv in ref["aux"]:
+        for p in lv["probs"]:
+            worst = max(worst, float(np.abs(aux["probs"][k].cpu().numpy() - p).max()))
+            k += 1
+    assert worst <= PROB_TOL, worst
+    # bitstream size
+    assert abs(len(blob) - len(ref_blob)) <= max(4, SIZE_TOL * len(ref_blob)), (len(blob), len(ref_blob))
+    # lossless round trip, decoded rows in the reference's order (oracle decode of its own file)
+    dec = codec.decode(bx, bo, streams).cpu().numpy()
+    assert dec.dtype == np.float32
+    assert np.array_equal(np.unique(dec.astype(np.int32), axis=0), np.unique(xyz, axis=0))
+    assert np.array_equal(dec, O.decode(ref_blob, w))
+
+
+@pytest.mark.parametrize("name", ["hac600", "blob", "hac2500"])
+def test_codec_vs_reference_golden(env, golden_dir, name):
+    """Against the fixtures produced by the reference's own driver (tests/golden/make_golden.py)."""
+    from gauspcc_b200 import bitstream
+    codec = env["codec"]
+    cg = np.load(os.path.join(golden_dir, "codec_golden.npz"))
+    xyz = cg[f"{name}_xyz"]
+    ref_blob = cg[f"{name}_bin"].tobytes()
+    blob, (bx, bo, streams), aux = _encode_file(codec, torch.tensor(xyz, dtype=torch.int32, device=codec.dev))
+    _, rbx, rbo, rstreams = bitstream.read_file(ref_blob)
+    assert np.array_equal(bx, rbx) and np.array_equal(bo, rbo) and len(streams) == len(rstreams)
+    assert abs(len(blob) - len(ref_blob)) <= max(4, SIZE_TOL * len(ref_blob))
+    if f"{name}_probs" in cg:
+        got = np.concatenate([p.cpu().numpy().reshape(-1) for p in aux["probs"]])
+        assert np.abs(got - cg[f"{name}_probs"]).max() <= PROB_TOL
+    dec = codec.decode(bx, bo, streams).cpu().numpy()
+    assert np.array_equal(dec, cg[f"{name}_decoded"])                    # same rows, same order as the reference run
+
+
+def test_edge_cases(env):
+    codec = env["codec"]
+    dev = codec.dev
+    rng = np.random.default_rng(9)
+    cases = [np.array([[5, -7, 9]], dtype=np.int32),                                   # single voxel
+             rng.integers(-40, 40, size=(40, 3)).astype(np.int32),                     # < 64: base level only
+             np.repeat(rng.integers(-400, 400, size=(500, 3)).astype(np.int32), 3, 0),  # duplicates merge
+             np.array([[-(1 << 20) + 16, 0, (1 << 20) - 16], [0, 0, 0]], dtype=np.int32)]  # extreme coordinates
+    for xyz in cases:
+        bx, bo, streams, _ = codec.encode(torch.tensor(xyz, device=dev))
+        dec = codec.decode(bx, bo, streams).cpu().numpy().astype(np.int32)
+        assert np.array_equal(np.unique(dec, axis=0), np.unique(xyz, axis=0))
+    with pytest.raises(ValueError):
+        codec.encode(torch.tensor([[0.25, 0, 0]], dtype=torch.float32, device=dev))
+    with pytest.raises(ValueError):
+        codec.encode(torch.tensor([[1 << 20, 0, 0]], dtype=torch.int32, device=dev))
+    with pytest.raises(ValueError):
+        codec.decode(np.zeros((1, 3), np.int32), np.array([1], np.uint8), [b"", b"", b""])
+
+
+def test_pcc_utils_api(env, tmp_path):
+    """The drop-in boundary: same call pattern as HAC's conduct_encoding/conduct_decoding
+    (scene/gaussian_model.py:1106-1121, 1248-1257)."""
+    from gauspcc_b200 import pcc_utils
+    from gauspcc_b200.synth import hac_like_cloud
+    from gauspcc_b200.weights import save_synthetic_checkpoint
+    ckpt = save_synthetic_checkpoint(str(tmp_path / "GausPcgc" / "best_model_ue_4stage_conv.pt"))
+    voxel = 0.001
+    xyz = hac_like_cloud(30000, 4)
+    anchor = torch.tensor(xyz, dtype=torch.float32, device=env["dev"]) * voxel
+    anchor_int = torch.round(anchor / voxel)
+    before = anchor_int.clone()
+    order = pcc_utils.calculate_morton_order(anchor_int)
+    anchor_int = anchor_int[order]
+    out = pcc_utils.compress_point_cloud(anchor_int, ckpt, str(tmp_path / "bits" / "xyz_pcc.bin"))
+    assert set(out) >= {"bpp", "enc_time", "file_size_bits", "num_points", "output_path"}
+    assert out["num_points"] == 30000 and out["file_size_bits"] == 8 * os.path.getsize(out["output_path"])
+    assert abs(out["bpp"] - out["file_size_bits"] / 30000) < 1e-9 and out["enc_time"] > 0
+    assert torch.equal(before[order], anchor_int)                         # input not mutated
+    dec = pcc_utils.decompress_point_cloud(out["output_path"], ckpt)
+    assert set(dec) >= {"dec_time", "num_points", "point_cloud", "output_path"}
+    pc = dec["point_cloud"]
+    assert pc.dtype == torch.float32 and pc.is_cuda and dec["num_points"] == 30000
+    order2 = pcc_utils.calculate_morton_order(pc)
+    assert torch.equal(pc[order2], anchor_int)                            # HAC re-sorts and gets the encoder's order back
+    # numpy input + posQ, is_data_pre_quantized=False mapping
+    out2 = pcc_utils.compress_point_cloud(xyz[:5000], ckpt, str(tmp_path / "b2" / "x.bin"))
+    d2 = pcc_utils.decompress_point_cloud(out2["output_path"], ckpt, is_data_pre_quantized=False)
+    want = (torch.tensor(xyz[:5000], dtype=torch.float32) - 131072) * 0.001
+    got = d2["point_cloud"].cpu()
+    assert torch.equal(got[pcc_utils.calculate_morton_order(got)], want[pcc_utils.calculate_morton_order(want)])
+    with pytest.raises(FileNotFoundError):
+        pcc_utils.compress_point_cloud(xyz[:100], str(tmp_path / "nope.pt"), str(tmp_path / "b3" / "x.bin"))
+    bad = str(tmp_path / "bad.pt")
+    torch.save({"prior_embedding.weight": torch.zeros(256, 32)}, bad)
+    with pytest.raises(RuntimeError):
+        pcc_utils.compress_point_cloud(xyz[:100], bad, str(tmp_path / "b4" / "x.bin"))
+
+
+def test_full_size_roundtrip_1m(env):
+    """BASELINE config 2 size: lossless round trip, encoder == decoder CDFs (else the range decoder
+    desynchronises and the geometry is garbage), teacher-forced decode == real decode."""
+    from gauspcc_b200.synth import hac_like_cloud
+    codec = env["codec"]
+    xyz = hac_like_cloud(1_000_000, 0)
+    x = torch.tensor(xyz, dtype=torch.float32, device=codec.dev)
+    bx, bo, streams, aux = codec.encode(x, collect=False)
+    dec = codec.decode(bx, bo, streams)
+    a = dec.to(torch.int64)
+    key = (a[:, 2] + (1 << 20)) * (1 << 42) + (a[:, 1] + (1 << 20)) * (1 << 21) + (a[:, 0] + (1 << 20))
+    b = x.to(torch.int64)
+    keyb = (b[:, 2] + (1 << 20)) * (1 << 42) + (b[:, 1] + (1 << 20)) * (1 << 21) + (b[:, 0] + (1 << 20))
+    assert torch.equal(torch.sort(key)[0], torch.sort(keyb)[0])
+    bits = 8 * sum(len(s) for s in streams)
+    assert 0 < bits / 1e6 < 200
