@@ -48,9 +48,21 @@ SIGNATURES = {
     "gpc_hash_lookup": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "gpc_kmap_dense": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "gpc_kmap_pairs_workspace_bytes": (c_sz, [c_i64, c_int]),
-    "gpc_kmap_pairs_count": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "gpc_kmap_pairs_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
-    "gpc_spconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp]),
+    "gpc_kmap_pairs_count": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_kmap_pairs_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gpc_spconv_pack_weights": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "gpc_spconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_spconv_fwd_v3": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_spconv_pack_weights_bf16": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "gpc_spconv_fwd_v4": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_spconv_pack_weights_frag": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "gpc_spconv_fwd_v5": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_spconv_fwd_v6": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_kmap_rt8_workspace_bytes": (c_sz, [c_i64]),
+    "gpc_kmap_rt8_count": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_kmap_rt8_fill": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gpc_spconv_fwd_v7": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_spconv_fwd_v8": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),

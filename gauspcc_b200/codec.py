@@ -40,8 +40,13 @@ class KMap:
     seg: torch.Tensor
     pair_nbr: torch.Tensor
     pair_row: torch.Tensor
+    pairs: Optional[torch.Tensor]
     n_pairs: int
     tile_rows: int
+    hdr: Optional[torch.Tensor] = None        # rt8 format (conv variants >= 50)
+    toff: Optional[torch.Tensor] = None
+    tiles: Optional[torch.Tensor] = None
+    n_tiles: int = 0
 
 
 @dataclass
@@ -63,6 +68,16 @@ class DeviceWeights:
         self.prior_emb = f("prior_embedding.weight")
         self.target_emb = f("target_embedding.target_res_embedding.weight")
         self.convs = torch.stack([f(k) for k in W.CONV_KEYS]).contiguous()           # [18,125,32,32]
+        self.convs_packed = torch.empty_like(self.convs)                             # [18,125,16,32,2] for the FFMA2 kernels
+        lib = _lib.load()
+        _lib.check(lib.gpc_spconv_pack_weights(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_packed),
+                                               C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights")
+        self.convs_frag = torch.empty_like(self.convs)                               # [18,125,2,2,2,32] uint4: mma A fragments of W^T
+        _lib.check(lib.gpc_spconv_pack_weights_frag(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_frag),
+                                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_frag")
+        self.convs_bf16 = torch.empty_like(self.convs)                               # [18,125,2,8,32] x (4 x bf16): hi / lo halves
+        _lib.check(lib.gpc_spconv_pack_weights_bf16(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_bf16),
+                                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_bf16")
         self.stage_emb = [None] + [f(f"pred_head_s{i}_emb.weight") for i in (1, 2, 3)]
         self.head = [tuple(f(f"pred_head_s{i}.{j}.{p}") for j, p in ((0, "weight"), (0, "bias"), (2, "weight"), (2, "bias")))
                      for i in range(4)]
@@ -76,7 +91,8 @@ class GausPcgcCodec:
         self.lib = _lib.load()
         self.dev = torch.device(device if device is not None else "cuda")
         self.w = weights
-        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 256))
+        self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 40))
+        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -202,18 +218,37 @@ class GausPcgcCodec:
         self._call("gpc_hash_build", _ptr(keys), n, _ptr(table), cap, self._stream())
         dense = self._empty((W.reference_layout()["prior_resnet.0.kernel"][0], n), torch.int32)
         self._call("gpc_kmap_dense", _ptr(table), cap, _ptr(keys), n, _ptr(dense), self._stream())
+        if 50 <= self.conv_variant < 60 and not keep_dense:
+            nst = (n + 63) // 64
+            hdr = self._empty((nst * 128,), torch.uint8)
+            toff = self._empty((nst * 126 + 1,), torch.int32)
+            cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
+            ws_b = self.lib.gpc_kmap_rt8_workspace_bytes(n)
+            ws = self._ws(ws_b)
+            self._call("gpc_kmap_rt8_count", _ptr(dense), n, _ptr(hdr), _ptr(toff), _ptr(cnt), _ptr(ws), ws_b, self._stream())
+            if self.conv_profile is not None:
+                cnt[1] = (dense >= 0).sum()               # bench only: true pair count for the roofline arithmetic
+            c = cnt.tolist()
+            n_tiles = int(c[0])
+            tl = self._empty((max(n_tiles, 1) * 8,), torch.int32)
+            self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
+            return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles)
         tr = self.tile_rows
         tiles = (n + tr - 1) // tr
         seg = self._empty((tiles * 126 + 1,), torch.int32)
         cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
         ws_b = self.lib.gpc_kmap_pairs_workspace_bytes(n, tr)
         ws = self._ws(ws_b)
-        self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
+        pad = 8 if (self.conv_variant >= 40 and not keep_dense) else 1
+        self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
         n_pairs = int(cnt.item())
-        pair_nbr = self._empty((max(n_pairs, 1),), torch.int32)
-        pair_row = self._empty((max(n_pairs, 1),), torch.int16)
-        self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), self._stream())
-        km = KMap(seg, pair_nbr, pair_row, n_pairs, tr)
+        split = self.conv_variant < 10 or keep_dense
+        pair_nbr = self._empty((max(n_pairs, 1),), torch.int32) if split else None
+        pair_row = self._empty((max(n_pairs, 1),), torch.int16) if split else None
+        pairs = self._empty((max(n_pairs, 1),), torch.int64) if self.conv_variant >= 10 else None
+        self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), _ptr(pairs),
+                   n_pairs if pad > 1 else 0, self._stream())
+        km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
         return (km, dense) if keep_dense else km
 
     def conv(self, x: torch.Tensor, widx: int, km: KMap, residual: Optional[torch.Tensor] = None, relu: bool = False,
@@ -223,8 +258,28 @@ class GausPcgcCodec:
         if self.conv_profile is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(self.dev))
-        self._call("gpc_spconv_fwd", _ptr(x), _ptr(self.w.convs[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_row), n,
-                   km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(y), self._stream())
+        wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
+        if self.conv_variant >= 60:
+            self._call("gpc_spconv_fwd_v8", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        elif self.conv_variant >= 50:
+            self._call("gpc_spconv_fwd_v7", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.toff), _ptr(km.hdr), _ptr(km.tiles), n,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        elif self.conv_variant >= 40:
+            self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        elif self.conv_variant >= 30:
+            self._call("gpc_spconv_fwd_v5", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        elif self.conv_variant >= 20:
+            self._call("gpc_spconv_fwd_v4", _ptr(x), _ptr(self.w.convs_bf16[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        elif self.conv_variant >= 10:
+            self._call("gpc_spconv_fwd_v3", _ptr(x), _ptr(wt), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows, _ptr(residual),
+                       1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        else:
+            self._call("gpc_spconv_fwd", _ptr(x), _ptr(wt), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_row), n,
+                       km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
         if self.conv_profile is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(self.dev))

@@ -101,7 +101,7 @@ extern "C" int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_
 // that the exclusive scan leaves seg[t*126+125] == start of tile t+1).
 constexpr int KP_THREADS = 256;
 
-__global__ void __launch_bounds__(KP_THREADS) kmap_pairs_count_kernel(const i32 *__restrict__ map, i64 n, int tile_rows,
+__global__ void __launch_bounds__(KP_THREADS) kmap_pairs_count_kernel(const i32 *__restrict__ map, i64 n, int tile_rows, int pad,
                                                                      u32 *__restrict__ counts) {
     __shared__ u32 cnt[GPC_K3 + 1];
     const i64 t = blockIdx.x;
@@ -116,14 +116,15 @@ __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_count_kernel(const i32 
         if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[k], c);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i <= GPC_K3; i += KP_THREADS) counts[t * (GPC_K3 + 1) + i] = cnt[i];
+    // pad > 1: every non-empty segment is rounded up to a multiple of `pad` entries (8-pair MMA tiles of one offset)
+    for (int i = threadIdx.x; i <= GPC_K3; i += KP_THREADS) counts[t * (GPC_K3 + 1) + i] = (cnt[i] + pad - 1) / pad * pad;
 }
 
 __global__ void kmap_total_kernel(const u32 *__restrict__ seg, i64 m, u32 *__restrict__ n_pairs) { *n_pairs = seg[m]; }
 
 __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_fill_kernel(const i32 *__restrict__ map, i64 n, int tile_rows,
                                                                     const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr,
-                                                                    u16 *__restrict__ pair_row) {
+                                                                    u16 *__restrict__ pair_row, u64 *__restrict__ pairs) {
     __shared__ u32 warp_cnt[KP_THREADS / 32];
     __shared__ u32 running;
     const i64 t = blockIdx.x;
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_fill_kernel(const i32 *
             for (int w = 0; w < warp; ++w) before += warp_cnt[w];
             if (nb >= 0) {
                 const u32 p = seg_begin + before + __popc(ballot & ((1u << lane) - 1u));
-                pair_nbr[p] = (u32)nb;
-                pair_row[p] = (u16)r;
+                if (pair_nbr) { pair_nbr[p] = (u32)nb; pair_row[p] = (u16)r; }
+                if (pairs) pairs[p] = (u64)(u32)nb | ((u64)(u32)r << 32) | ((u64)(u32)k << 48);
             }
             __syncthreads();
             if (threadIdx.x == 0) { u32 tot = 0; for (int w = 0; w < KP_THREADS / 32; ++w) tot += warp_cnt[w]; running += tot; }
@@ -160,17 +161,17 @@ extern "C" size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows) {
     const i64 m = tiles * (GPC_K3 + 1);
     return align_up((size_t)m * 4, 256) + align_up(scan_workspace_bytes<u32>(m), 256) + 1024;
 }
-extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, uint32_t *n_pairs,
+extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, int pad, uint32_t *seg, uint32_t *n_pairs,
                                     void *ws, size_t ws_bytes, void *stream) {
     cudaStream_t st = as_stream(stream);
-    GPC_REQUIRE(tile_rows > 0 && tile_rows <= 65536, GPC_EINVAL, "tile_rows must be in 1..65536");
+    GPC_REQUIRE(tile_rows > 0 && tile_rows <= 65536 && pad >= 1, GPC_EINVAL, "tile_rows must be in 1..65536, pad >= 1");
     if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 4, st)); return GPC_OK; }
     GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_pairs_workspace_bytes(n, tile_rows), GPC_ENOSPC, "workspace too small");
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
     const i64 m = tiles * (GPC_K3 + 1);
     u32 *counts = (u32 *)ws;
     void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
-    kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, counts);
+    kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{counts};
     int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, seg, scan_ws, st);      // seg has m+1 entries
@@ -180,10 +181,94 @@ extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows
     return GPC_OK;
 }
 extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr,
-                                   uint16_t *pair_row, void *stream) {
+                                   uint16_t *pair_row, uint64_t *pairs, int64_t n_entries, void *stream) {
     if (n <= 0) return GPC_OK;
+    // padded streams: entries not written below stay INVALID (all ones)
+    if (pairs && n_entries > 0) GPC_CUDA_CHECK(cudaMemsetAsync(pairs, 0xFF, (size_t)n_entries * 8, as_stream(stream)));
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
-    kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, as_stream(stream)>>>(map, n, tile_rows, seg, pair_nbr, pair_row);
+    kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, as_stream(stream)>>>(map, n, tile_rows, seg, pair_nbr, pair_row, pairs);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+
+// ---------------------------------------------------------------- row-tied 8-row tiles ("rt8") for spconv v7
+// Sub-tile = 64 consecutive output rows = 8 groups of 8 rows.  For every (sub-tile, offset k) the header byte
+// says which groups have at least one neighbour at k; every such group gets one 8-entry tile: entry g = input
+// row of (output row 8j+g) + d_k, or 0xFFFFFFFF.  Tiles of a sub-tile are stored in (k, group) order;
+// toff[st*126 + k] = index of the first tile of (st, k) (exclusive scan, toff[st*126+125] = next sub-tile).
+constexpr int RT_TW = 64;
+
+__device__ __forceinline__ u32 rt8_mask(const i32 *__restrict__ map, i64 n, i64 r0, int k, int lane, i32 &v0, i32 &v1) {
+    const i64 ra = r0 + lane, rb = r0 + 32 + lane;
+    v0 = ra < n ? map[(i64)k * n + ra] : -1;
+    v1 = rb < n ? map[(i64)k * n + rb] : -1;
+    const u32 b0 = __ballot_sync(0xFFFFFFFFu, v0 >= 0), b1 = __ballot_sync(0xFFFFFFFFu, v1 >= 0);
+    u32 m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if ((b0 >> (8 * j)) & 0xFFu) m |= 1u << j;
+        if ((b1 >> (8 * j)) & 0xFFu) m |= 1u << (4 + j);
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256) kmap_rt8_count_kernel(const i32 *__restrict__ map, i64 n, u8 *__restrict__ hdr,
+                                                            u32 *__restrict__ counts) {
+    const i64 st = blockIdx.x;
+    const i64 r0 = st * RT_TW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < 128; k += 8) {
+        u32 m = 0;
+        if (k < GPC_K3) { i32 v0, v1; m = rt8_mask(map, n, r0, k, lane, v0, v1); }
+        if (lane == 0) {
+            hdr[st * 128 + k] = (u8)m;
+            if (k <= GPC_K3) counts[st * (GPC_K3 + 1) + k] = __popc(m);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) kmap_rt8_fill_kernel(const i32 *__restrict__ map, i64 n, const u32 *__restrict__ toff,
+                                                           u32 *__restrict__ tiles) {
+    const i64 st = blockIdx.x;
+    const i64 r0 = st * RT_TW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < GPC_K3; k += 8) {
+        i32 v0, v1;
+        const u32 m = rt8_mask(map, n, r0, k, lane, v0, v1);
+        if (!m) continue;
+        const u32 base = toff[st * (GPC_K3 + 1) + k];
+        const int j0 = lane >> 3, j1 = 4 + (lane >> 3);
+        if ((m >> j0) & 1u) tiles[(i64)(base + __popc(m & ((1u << j0) - 1u))) * 8 + (lane & 7)] = (u32)v0;   // -1 -> 0xFFFFFFFF
+        if ((m >> j1) & 1u) tiles[(i64)(base + __popc(m & ((1u << j1) - 1u))) * 8 + (lane & 7)] = (u32)v1;
+    }
+}
+extern "C" size_t gpc_kmap_rt8_workspace_bytes(int64_t n) {
+    const i64 nst = n > 0 ? (n + RT_TW - 1) / RT_TW : 1;
+    const i64 m = nst * (GPC_K3 + 1);
+    return align_up((size_t)m * 4, 256) + align_up(scan_workspace_bytes<u32>(m), 256) + 1024;
+}
+extern "C" int gpc_kmap_rt8_count(const int32_t *map, int64_t n, uint8_t *hdr, uint32_t *toff, uint32_t *n_tiles, void *ws,
+                                  size_t ws_bytes, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(n_tiles, 0, 4, st)); return GPC_OK; }
+    GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_rt8_workspace_bytes(n), GPC_ENOSPC, "workspace too small");
+    const i64 nst = (n + RT_TW - 1) / RT_TW;
+    const i64 m = nst * (GPC_K3 + 1);
+    u32 *counts = (u32 *)ws;
+    void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
+    kmap_rt8_count_kernel<<<(unsigned)nst, 256, 0, st>>>(map, n, hdr, counts);
+    GPC_LAUNCH_CHECK();
+    PtrLoad<u32> pl{counts};
+    int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, toff, scan_ws, st);
+    if (rc) return rc;
+    kmap_total_kernel<<<1, 1, 0, st>>>(toff, m, n_tiles);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+extern "C" int gpc_kmap_rt8_fill(const int32_t *map, int64_t n, const uint32_t *toff, uint32_t *tiles, void *stream) {
+    if (n <= 0) return GPC_OK;
+    const i64 nst = (n + RT_TW - 1) / RT_TW;
+    kmap_rt8_fill_kernel<<<(unsigned)nst, 256, 0, as_stream(stream)>>>(map, n, toff, tiles);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }

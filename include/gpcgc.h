@@ -115,18 +115,67 @@ int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, in
  * pair_nbr = input row, pair_row = output row - t*tile_rows.  Two calls: count (fills seg as an
  * exclusive scan, *n_pairs device u32), then fill. */
 size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows);
-int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, uint32_t *n_pairs,
+/* pad >= 1: every non-empty (tile, offset) segment is rounded up to a multiple of `pad` entries; the
+ * padding entries of the combined stream are all-ones (INVALID).  *n_pairs counts padded entries. */
+int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, int pad, uint32_t *seg, uint32_t *n_pairs,
                          void *ws, size_t ws_bytes, void *stream);
+/* fill writes the split arrays (pair_nbr/pair_row, may be NULL) and/or the combined stream
+ * pairs[p] = nbr | row_in_tile << 32 | k << 48 (may be NULL) consumed by gpc_spconv_fwd_v3 */
 int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg,
-                        uint32_t *pair_nbr, uint16_t *pair_row, void *stream);
+                        uint32_t *pair_nbr, uint16_t *pair_row, uint64_t *pairs, int64_t n_entries, void *stream);
 
 /* ---- a-7/a-10/a-12: sparse conv (spnn.Conv3d(32,32,5), bias-less) ---- */
 /* y[o,:] = act( sum_k x[nbr_k(o),:] . W[k] (+ residual[o,:]) ); W [125,32,32] fp32;
  * offsets accumulate in ascending k for every row (deterministic). flags: bit0 = ReLU. */
 #define GPC_CONV_RELU 1
+/* variant 0: unpipelined FFMA kernel, W in the reference layout [125,32,32].
+ * variant >= 1: cp.async-pipelined FFMA2 kernels; W must be the packed form produced by
+ * gpc_spconv_pack_weights ([125,16,32] float2 = (W[2i][co], W[2i+1][co])).
+ * tile_rows must match the pair lists (gpc_kmap_pairs_*). */
+int gpc_spconv_pack_weights(const float *W, int n_kernels, float *W_packed, void *stream);
 int gpc_spconv_fwd(const float *x, const float *W, const uint32_t *seg, const uint32_t *pair_nbr,
                    const uint16_t *pair_row, int64_t n, int tile_rows, const float *residual,
-                   int flags, float *y, void *stream);
+                   int flags, float *y, int variant, void *stream);
+
+/* v3 kernels (variant 10..): fixed-size gather blocks over the combined pair stream, warp-owned rows */
+int gpc_spconv_fwd_v3(const float *x, const float *W_packed, const uint32_t *seg, const uint64_t *pairs,
+                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                      void *stream);
+
+/* v4 kernels (variant 20..): one warp per sub-tile of `tile_rows` rows, split-bf16 mma.sync contraction
+ * with fp32 accumulation; Wb from gpc_spconv_pack_weights_bf16 ([125][2][8][32] x 4 bf16, hi and lo halves) */
+int gpc_spconv_pack_weights_bf16(const float *W, int n_kernels, void *Wb, void *stream);
+int gpc_spconv_fwd_v4(const float *x, const void *Wb, const uint32_t *seg, const uint64_t *pairs,
+                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                      void *stream);
+
+/* v5 kernels (variant 30..): as v4 with W^T as the MMA A operand (8-pair granularity);
+ * Wa from gpc_spconv_pack_weights_frag ([125][2][2][2][32] uint4 fragment order) */
+int gpc_spconv_pack_weights_frag(const float *W, int n_kernels, void *Wa, void *stream);
+int gpc_spconv_fwd_v5(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
+                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                      void *stream);
+
+/* v6 kernels (variant 40..): software-pipelined v5 over a stream padded to 8-entry tiles (pad = 8) */
+int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
+                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                      void *stream);
+
+/* row-tied kernel map ("rt8") + v7 conv (variant 50..): sub-tiles of 64 rows = 8 groups of 8 rows;
+ * hdr[st*128 + k] = mask of groups with a neighbour at offset k; toff[st*126 + k] = first 8-entry tile of
+ * (st,k) in `tiles` (u32 input rows, 0xFFFFFFFF = absent); accumulators stay in registers */
+size_t gpc_kmap_rt8_workspace_bytes(int64_t n);
+int gpc_kmap_rt8_count(const int32_t *map, int64_t n, uint8_t *hdr, uint32_t *toff, uint32_t *n_tiles,
+                       void *ws, size_t ws_bytes, void *stream);
+int gpc_kmap_rt8_fill(const int32_t *map, int64_t n, const uint32_t *toff, uint32_t *tiles, void *stream);
+int gpc_spconv_fwd_v7(const float *x, const void *Wa, const uint32_t *toff, const uint8_t *hdr,
+                      const uint32_t *tiles, int64_t n, const float *residual, int flags, float *y,
+                      int variant, void *stream);
+
+/* v8 (variant 60): v6 with the per-tile instruction count cut (ping-pong register sets, 32-bit shared addressing) */
+int gpc_spconv_fwd_v8(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
+                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                      void *stream);
 
 /* ---- a-6/a-9/a-12: embeddings ---- */
 /* out[o,:] = table[idx[o],:]  (prior_embedding, network_ue_4stage_conv.py:15) */

@@ -2,10 +2,11 @@
 # One gpurun call: GPU parity tests, smoke, a short bench.  Outputs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+if [ -n "${PRE_CMD}" ]; then bash -c "${PRE_CMD}" > gpurun_out/pre.log 2>&1; tail -60 gpurun_out/pre.log; fi
 timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -40 gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-tail -5 gpurun_out/smoke.log
+tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 3 --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
-tail -15 gpurun_out/bench.log
+tail -6 gpurun_out/bench.log
