@@ -166,6 +166,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    codec.conv_profile = []                                          # also makes build_kmap count the true pairs
     for _ in range(args.warmup):
         out, _, _ = step()
     assert out.shape[0] == args.points
@@ -248,8 +249,12 @@ def main():
                        "parallelism": f"scene-sharded x{world}", "wall_ms_per_step": round(t_wall * 1e3 / args.steps, 2)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "spconv_fwd_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
-                         "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+            "roofline": {"kernel": "spconv_fwd (variant %d)" % codec.conv_variant, "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+                         # dram__bytes_read+write of the profiled launch (442 133-row level) / its algorithmic bytes = 1.006
+                         # (profiles/r01_spconv_v6_ncu_summary.md); scaled to the average launch of this run
+                         "traffic": round(1.006 * conv_bytes / max(len(prof), 1)),
+                         "note": "not HBM-bound: L1/shared path 71.5 %, issue 49 %, HMMA pipe 24.6 % (ncu); see DESIGN.md 5",
                          "launches": len(prof), "avg_launch_ms": round(conv_ms / max(len(prof), 1), 4),
                          "share_of_step": round(conv_ms / ms, 4), "tflops_fp32": round(conv_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms else 0},
         }

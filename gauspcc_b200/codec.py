@@ -47,6 +47,7 @@ class KMap:
     toff: Optional[torch.Tensor] = None
     tiles: Optional[torch.Tensor] = None
     n_tiles: int = 0
+    n_real: int = 0                           # true (row, neighbour) pairs -- filled in bench profiling mode only
 
 
 @dataclass
@@ -232,7 +233,7 @@ class GausPcgcCodec:
             n_tiles = int(c[0])
             tl = self._empty((max(n_tiles, 1) * 8,), torch.int32)
             self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
-            return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles)
+            return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
         tr = self.tile_rows
         tiles = (n + tr - 1) // tr
         seg = self._empty((tiles * 126 + 1,), torch.int32)
@@ -249,6 +250,7 @@ class GausPcgcCodec:
         self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), _ptr(pairs),
                    n_pairs if pad > 1 else 0, self._stream())
         km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
+        km.n_real = int((dense >= 0).sum().item()) if self.conv_profile is not None else n_pairs
         return (km, dense) if keep_dense else km
 
     def conv(self, x: torch.Tensor, widx: int, km: KMap, residual: Optional[torch.Tensor] = None, relu: bool = False,
@@ -284,7 +286,7 @@ class GausPcgcCodec:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(self.dev))
             # per layer n*C*4*2 + pairs*8 + K^3*C^2*4 bytes and 2*pairs*C^2 FLOP
-            self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_pairs * 8 + 125 * 32 * 32 * 4, 2 * km.n_pairs * 32 * 32))
+            self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
         return y
 
     def res_stack(self, x: torch.Tensor, ids, km: KMap) -> torch.Tensor:

@@ -156,6 +156,59 @@ __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_fill_kernel(const i32 *
     }
 }
 
+
+// ---- warp-per-tile variants for small tiles (tile_rows = 32 * RPL, RPL = 1, 2, 4): no block barriers, each warp
+// streams its tile's 125 x tile_rows slice of the dense map with coalesced loads and ballots (the block-per-tile
+// kernels above spend their time in 125 x 3 __syncthreads with a quarter of the threads idle when tiles are small).
+template <int RPL>
+__global__ void __launch_bounds__(128) kmap_pairs_count_warp_kernel(const i32 *__restrict__ map, i64 n, i64 tiles, int pad,
+                                                                   u32 *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const i64 t = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= tiles) return;
+    const i64 r0 = t * (32 * RPL);
+#pragma unroll 5
+    for (int k = 0; k < GPC_K3; ++k) {
+        u32 c = 0;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const i64 r = r0 + i * 32 + lane;
+            const bool v = r < n && map[(i64)k * n + r] >= 0;
+            c += __popc(__ballot_sync(0xFFFFFFFFu, v));
+        }
+        c = (c + pad - 1) / pad * pad;
+        if (lane == 0) counts[t * (GPC_K3 + 1) + k] = c;
+    }
+    if (lane == 0) counts[t * (GPC_K3 + 1) + GPC_K3] = 0;
+}
+
+template <int RPL>
+__global__ void __launch_bounds__(128) kmap_pairs_fill_warp_kernel(const i32 *__restrict__ map, i64 n, i64 tiles,
+                                                                  const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr,
+                                                                  u16 *__restrict__ pair_row, u64 *__restrict__ pairs) {
+    const int lane = threadIdx.x & 31;
+    const i64 t = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= tiles) return;
+    const i64 r0 = t * (32 * RPL);
+    const u32 lt = (1u << lane) - 1u;
+#pragma unroll 5
+    for (int k = 0; k < GPC_K3; ++k) {
+        u32 p = seg[t * (GPC_K3 + 1) + k];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const i64 r = r0 + i * 32 + lane;
+            const i32 nb = r < n ? map[(i64)k * n + r] : -1;
+            const u32 bal = __ballot_sync(0xFFFFFFFFu, nb >= 0);
+            if (nb >= 0) {
+                const u32 q = p + __popc(bal & lt);
+                if (pair_nbr) { pair_nbr[q] = (u32)nb; pair_row[q] = (u16)(i * 32 + lane); }
+                if (pairs) pairs[q] = (u64)(u32)nb | ((u64)(u32)(i * 32 + lane) << 32) | ((u64)(u32)k << 48);
+            }
+            p += __popc(bal);
+        }
+    }
+}
+
 extern "C" size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows) {
     const i64 tiles = n > 0 ? (n + tile_rows - 1) / tile_rows : 1;
     const i64 m = tiles * (GPC_K3 + 1);
@@ -171,7 +224,10 @@ extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows
     const i64 m = tiles * (GPC_K3 + 1);
     u32 *counts = (u32 *)ws;
     void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
-    kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts);
+    if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts);
+    else if (tile_rows == 64) kmap_pairs_count_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts);
+    else if (tile_rows == 128) kmap_pairs_count_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts);
+    else kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{counts};
     int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, seg, scan_ws, st);      // seg has m+1 entries
@@ -186,7 +242,11 @@ extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows,
     // padded streams: entries not written below stay INVALID (all ones)
     if (pairs && n_entries > 0) GPC_CUDA_CHECK(cudaMemsetAsync(pairs, 0xFF, (size_t)n_entries * 8, as_stream(stream)));
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
-    kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, as_stream(stream)>>>(map, n, tile_rows, seg, pair_nbr, pair_row, pairs);
+    cudaStream_t st = as_stream(stream);
+    if (tile_rows == 32) kmap_pairs_fill_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 64) kmap_pairs_fill_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 128) kmap_pairs_fill_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, seg, pair_nbr, pair_row, pairs);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
