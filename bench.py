@@ -219,6 +219,7 @@ def main():
             r = pcc_utils.compress_point_cloud(x_host, ckpt, binp)
             d2h_enc = codec_stats(pcc_utils)
             d = pcc_utils.decompress_point_cloud(binp, ckpt)
+            dec_stats = codec_stats(pcc_utils)
             pts_host = d["point_cloud"].cpu()                        # the step's result read back to the host
             torch.cuda.synchronize(dev)
             dt = time.perf_counter() - t0
@@ -230,8 +231,10 @@ def main():
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {"value": round(total_points / float(tw.item()) / 1e6, 4), "unit": UNIT,
                "h2d_bytes_per_step": int(x_host.numel() * 4 + rows * 4),                       # input + decoded symbols
-               "d2h_bytes_per_step": int(2 * rows * 2 * 28 + rows * 4 + pts_host.numel() * 4),    # CDF rows (enc+dec) + symbols + result
+               "d2h_bytes_per_step": int(rows * 4 * 4 + rows * 2 * 28 + pts_host.numel() * 4),  # enc (c_low,c_high) words + dec CDF rows + result
                "enc_s": round(r["enc_time"], 4), "dec_s": round(d["dec_time"], 4), "bpp": round(r["bpp"], 3),
+               "dec_host_ac_s": round(dec_stats.get("host_ac_s", 0.0), 4), "dec_gpu_wait_s": round(dec_stats.get("gpu_wait_s", 0.0), 4),
+               "dec_gpu_s": round(dec_stats.get("gpu_ms", 0.0) / 1e3, 4),
                "ac_threads": codec.pool._max_workers}
         assert pts_host.shape[0] == args.points
 

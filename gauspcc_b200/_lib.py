@@ -67,10 +67,12 @@ SIGNATURES = {
     "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),
     "gpc_head_cdf": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "gpc_head_cdf_sym": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gpc_split_symbol": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "gpc_merge_symbol": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "gpc_ac_encode_h": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, C.POINTER(c_i64)]),
     "gpc_ac_decode_h": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
+    "gpc_ac_encode_lohi_h": (c_int, [c_vp, c_i64, c_vp, c_i64, C.POINTER(c_i64)]),
 }
 
 _lib = None

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -237,12 +238,12 @@ class GausPcgcCodec:
         tr = self.tile_rows
         tiles = (n + tr - 1) // tr
         seg = self._empty((tiles * 126 + 1,), torch.int32)
-        cnt = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
         ws_b = self.lib.gpc_kmap_pairs_workspace_bytes(n, tr)
         ws = self._ws(ws_b)
         pad = 8 if (self.conv_variant >= 40 and not keep_dense) else 1
         self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
-        n_pairs = int(cnt.item())
+        n_pairs, n_real = (int(v) for v in cnt.tolist())
         split = self.conv_variant < 10 or keep_dense
         pair_nbr = self._empty((max(n_pairs, 1),), torch.int32) if split else None
         pair_row = self._empty((max(n_pairs, 1),), torch.int16) if split else None
@@ -250,7 +251,7 @@ class GausPcgcCodec:
         self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), _ptr(pairs),
                    n_pairs if pad > 1 else 0, self._stream())
         km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
-        km.n_real = int((dense >= 0).sum().item()) if self.conv_profile is not None else n_pairs
+        km.n_real = n_real
         return (km, dense) if keep_dense else km
 
     def conv(self, x: torch.Tensor, widx: int, km: KMap, residual: Optional[torch.Tensor] = None, relu: bool = False,
@@ -312,9 +313,11 @@ class GausPcgcCodec:
         u = self.res_stack(u0, W.TARGET_CONVS, child.kmap)
         return child, u
 
-    def stage_cdf(self, u: torch.Tensor, occ_partial: Optional[torch.Tensor], i: int, km: KMap, cdf_out: torch.Tensor,
-                  prob_out: Optional[torch.Tensor] = None):
-        """stage i: (+ context embedding) -> spatial_conv_s{i} -> pred_head_s{i} -> uint16 CDF rows."""
+    def stage_cdf(self, u: torch.Tensor, occ_partial: Optional[torch.Tensor], i: int, km: KMap, cdf_out: Optional[torch.Tensor],
+                  prob_out: Optional[torch.Tensor] = None, lohi_out: Optional[torch.Tensor] = None):
+        """stage i: (+ context embedding) -> spatial_conv_s{i} -> pred_head_s{i} -> uint16 CDF rows.
+        Encoder: lohi_out given => occ_partial is the TRUE occupancy, the stage's symbol is split off inside the head kernel
+        and only (c_low, c_high) of that symbol is written (4 B per row for the host coder)."""
         n = u.shape[0]
         if i == 0:
             f = u
@@ -326,8 +329,12 @@ class GausPcgcCodec:
         t = self.conv(f, c0, km, relu=True)
         t = self.conv(t, c1, km)
         w1, b1, w2, b2 = self.w.head[i]
-        self._call("gpc_head_cdf", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(cdf_out),
-                   _ptr(prob_out), self._stream())
+        if lohi_out is not None:
+            self._call("gpc_head_cdf_sym", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(occ_partial),
+                       STAGE_SHIFT[i], _ptr(lohi_out), _ptr(cdf_out), _ptr(prob_out), self._stream())
+        else:
+            self._call("gpc_head_cdf", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(cdf_out),
+                       _ptr(prob_out), self._stream())
 
     # ------------------------------------------------------------------ host range coder
     def _ac_encode(self, cdf: np.ndarray, sym: np.ndarray) -> bytes:
@@ -337,6 +344,17 @@ class GausPcgcCodec:
         ln = C.c_int64(0)
         _lib.check(self.lib.gpc_ac_encode_h(cdf.ctypes.data_as(C.c_void_p), sym.ctypes.data_as(C.c_void_p), n, Lp,
                                             out.ctypes.data_as(C.c_void_p), cap, C.byref(ln)), "gpc_ac_encode_h")
+        return out[:ln.value].tobytes()
+
+    def _ac_encode_lohi(self, lohi: np.ndarray, ready: Optional[torch.cuda.Event] = None) -> bytes:
+        if ready is not None:
+            ready.synchronize()                        # the level's D2H copies have landed (GPU keeps running later levels)
+        n = lohi.shape[0]
+        cap = 4 * n + 64
+        out = np.empty(cap, dtype=np.uint8)
+        ln = C.c_int64(0)
+        _lib.check(self.lib.gpc_ac_encode_lohi_h(lohi.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), cap,
+                                                 C.byref(ln)), "gpc_ac_encode_lohi_h")
         return out[:ln.value].tobytes()
 
     def _ac_decode(self, cdf: np.ndarray, stream: bytes, sym_out: np.ndarray):
@@ -367,9 +385,9 @@ class GausPcgcCodec:
         levels = self.build_pyramid(leaf, mm.astype(np.int64))
         L = len(levels) - 1
         rows = sum(l.n for l in levels[1:])
-        arena = self._pin(rows * (2 * (3 + 3 + 5 + 17) + 4) + 64 * 4 * max(L, 1) + 4096) if download else None
+        arena = self._pin(rows * 16 + 64 * 4 * max(L, 1) + 4096) if download else None
         cursor = 0
-        jobs = []          # (cdf_np, sym_np)
+        futs = []
         aux = {"levels": levels, "probs": [], "cdfs": []} if (collect or not download) else None
 
         def carve(nbytes, dtype, shape):
@@ -385,22 +403,25 @@ class GausPcgcCodec:
             gt.kmap = child.kmap                       # same coordinate set: reuse for the next prior stack
             if collect:
                 aux.setdefault("child_keys", []).append(child.keys)
+            level_jobs = []
             for i in range(4):
                 A = W.STAGE_ALPHABETS[i]
-                cdf_d = self._empty((gt.n, A + 1), torch.int16)
+                cdf_d = self._empty((gt.n, A + 1), torch.int16) if collect else None
                 prob_d = self._empty((gt.n, A), torch.float32) if collect else None
-                self.stage_cdf(u, gt.occ, i, child.kmap, cdf_d, prob_d)
-                sym_d = self._empty((gt.n,), torch.uint8)
-                self._call("gpc_split_symbol", _ptr(gt.occ), gt.n, STAGE_SHIFT[i], STAGE_MASK[i], _ptr(sym_d), self._stream())
+                lohi_d = self._empty((gt.n,), torch.int32)
+                self.stage_cdf(u, gt.occ, i, child.kmap, cdf_d, prob_d, lohi_out=lohi_d)
                 if download:
-                    cdf_h = carve(gt.n * (A + 1) * 2, torch.int16, (gt.n, A + 1))
-                    sym_h = carve(gt.n, torch.uint8, (gt.n,))
-                    cdf_h.copy_(cdf_d, non_blocking=True)
-                    sym_h.copy_(sym_d, non_blocking=True)
-                    jobs.append((cdf_h, sym_h))
+                    lohi_h = carve(gt.n * 4, torch.int32, (gt.n,))
+                    lohi_h.copy_(lohi_d, non_blocking=True)
+                    level_jobs.append(lohi_h)
                 if collect:
                     aux["probs"].append(prob_d)
                     aux["cdfs"].append(cdf_d)
+            if download:
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(self.dev))
+                # host range coding of this level overlaps the GPU work of the finer levels
+                futs += [self.pool.submit(self._ac_encode_lohi, h.numpy().view(np.uint32), ready) for h in level_jobs]
         base = levels[0]
         base_xyz = self._empty((base.n, 3), torch.int32)
         self._call("gpc_unpack_keys_i32", _ptr(base.keys), base.n, _ptr(base_xyz), self._stream())
@@ -408,10 +429,7 @@ class GausPcgcCodec:
         base_occ_h = base.occ.cpu().numpy()
         self._seg_end()
         gpu_ms = self._seg_total_ms()                  # synchronises: all D2H copies have landed
-        streams = None
-        if download:
-            futs = [self.pool.submit(self._ac_encode, c.numpy().view(np.uint16), s.numpy()) for c, s in jobs]
-            streams = [f.result() for f in futs]
+        streams = [f.result() for f in futs] if download else None
         self.last_stats = {"gpu_ms": gpu_ms, "launches": self.launches, "rows": rows, "levels": L,
                            "d2h_bytes": cursor, "n_unique": int(leaf.shape[0])}
         return base_xyz_h, base_occ_h, streams, aux
@@ -445,6 +463,7 @@ class GausPcgcCodec:
         self._call("gpc_sort_pairs", _ptr(keys), _ptr(None), _ptr(skeys), _ptr(perm), n0, xf, _ptr(ws), ws_b, self._stream())
         cur = Level(skeys, bo[perm.long()] if n0 else bo, n0)
         pin = None
+        t_wait = t_ac = 0.0
         for g in range(0, len(streams), 4):
             n_child = int(np.unpackbits(cur.occ.cpu().numpy()).sum()) if forced_occ is None else int(forced_occ[g // 4].shape[0])
             child, u = self.level_features(cur, n_child)
@@ -463,9 +482,13 @@ class GausPcgcCodec:
                     cdf_h = pin[:n_child * (A + 1) * 2].view(torch.int16).view(n_child, A + 1)
                     cdf_h.copy_(cdf_d, non_blocking=True)
                     self._seg_end()
+                    t0 = time.perf_counter()
                     torch.cuda.current_stream(self.dev).synchronize()
+                    t1 = time.perf_counter()
                     sym_h = pin[n_child * 36:n_child * 37]
                     self._ac_decode(cdf_h.numpy().view(np.uint16), streams[g + i], sym_h.numpy())
+                    t_wait += t1 - t0
+                    t_ac += time.perf_counter() - t1
                     self._seg_begin()
                     sym_d = sym_h.to(self.dev, non_blocking=True)
                 self._call("gpc_merge_symbol", _ptr(occ), n_child, STAGE_SHIFT[i], _ptr(sym_d), self._stream())
@@ -478,7 +501,7 @@ class GausPcgcCodec:
         self._call("gpc_expand_leaves_f32", _ptr(cur.keys), _ptr(cur.occ), cur.n, n_pts, float(scale), _ptr(out), _ptr(ws), ws_b,
                    self._stream())
         self._seg_end()
-        self.last_stats = {"gpu_ms": self._seg_total_ms(), "launches": self.launches}
+        self.last_stats = {"gpu_ms": self._seg_total_ms(), "launches": self.launches, "host_ac_s": t_ac, "gpu_wait_s": t_wait}
         return out
 
 

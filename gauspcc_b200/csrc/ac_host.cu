@@ -7,7 +7,11 @@
 // arithmetic_kernel.cu:58-91,114-162 (encode) and :237-287,310-355 (decode).  A CDF row has Lp uint16
 // entries; the last one is never read (the top of the last symbol is 0x10000).  This is product code
 // (the CPU oracle under oracle/ has its own, separate restatement).
+#include <string.h>
 #include "common.cuh"
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -90,48 +94,187 @@ extern "C" int gpc_ac_encode_h(const uint16_t *cdf, const uint8_t *sym, int64_t 
     return GPC_OK;
 }
 
+// ---- fast paths -------------------------------------------------------------------------------------------------
+// Same arithmetic as above, restructured for throughput: the renormalisation shifts out ALL leading bits on which
+// low and high agree in one step (count-leading-zeros of low ^ high) instead of one per loop trip, bits are pulled
+// from a 64-bit reservoir, and the decoder's 64-bit division is a double-precision divide with an exact +-1 fix-up.
+namespace {
+
+struct BitReservoir {
+    const u8 *in;
+    i64 len, pos;
+    u64 buf;          // MSB-aligned, `have` valid bits (zeros past the end of the stream)
+    int have;
+    inline void refill() {
+        if (pos + 8 <= len) {                    // bulk: splice 8 big-endian bytes behind the valid bits, keep whole bytes only
+            u64 w;
+            memcpy(&w, in + pos, 8);
+            w = __builtin_bswap64(w);
+            buf |= have ? (w >> have) : w;
+            const int adv = (63 - have) >> 3;
+            pos += adv;
+            have += adv * 8;
+        } else {
+            while (have <= 56) {
+                const u64 byte = pos < len ? in[pos] : 0;
+                ++pos;
+                buf |= byte << (56 - have);
+                have += 8;
+            }
+        }
+    }
+    inline u32 take(int s) {       // 0 <= s <= 32; caller keeps have >= 32 by refilling once per symbol
+        const u32 r = (u32)((buf >> 32) >> (32 - s));
+        buf <<= s;
+        have -= s;
+        return r;
+    }
+};
+
+struct FastWriter {
+    u8 *out;
+    i64 cap, len;
+    u64 acc;          // `n` pending output bits, right-aligned
+    int n;
+    bool overflow;
+    inline void put_bits(u32 v, int s) {      // s <= 32
+        acc = (acc << s) | v;
+        n += s;
+        while (n >= 8) {
+            n -= 8;
+            if (len < cap) out[len] = (u8)(acc >> n); else overflow = true;
+            ++len;
+        }
+    }
+    inline void put_run(u32 bit, u64 count) {  // `count` copies of `bit`
+        const u32 pat = bit ? 0xFFFFFFFFu : 0u;
+        while (count >= 32) { put_bits(pat, 32); count -= 32; }
+        if (count) put_bits(pat >> (32 - (int)count), (int)count);
+    }
+};
+
+}  // namespace
+
+// Decoder, division-free: torchac picks the symbol by count = floor(num / span) and a binary search for the largest m
+// with cdf[m] <= count.  floor(num/span) >= cdf[m]  <=>  cdf[m] * span <= num, so the symbol is the number of entries
+// cdf[1..Lp-2] whose product with span is <= num -- multiplications (independent, SIMD for the 16-ary stage) replace the
+// 64-bit division that heads the serial dependency chain of every symbol, and the products are the very terms the
+// interval update needs ((span * c) >> 16).  Renormalisation shifts out the whole common prefix of low/high at once.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static inline int sym16_avx2(const u16 *row, u64 span, u64 num) {
+    // prod[m] = row[m] * span for m = 0..15 (row[0] == 0), span = (span-1) + 1 with span-1 < 2^32
+    const __m256i sm1 = _mm256_set1_epi64x((long long)(span - 1));
+    const __m256i nv = _mm256_set1_epi64x((long long)num);
+    int s = 0;
+#pragma GCC unroll 4
+    for (int v = 0; v < 4; ++v) {
+        const __m128i r16 = _mm_loadl_epi64((const __m128i *)(row + 4 * v));          // 4 x u16
+        const __m256i r64 = _mm256_cvtepu16_epi64(r16);
+        const __m256i p = _mm256_add_epi64(_mm256_mul_epu32(r64, sm1), r64);
+        const __m256i gt = _mm256_cmpgt_epi64(p, nv);                                   // product > num  (values < 2^50: signed ok)
+        s += 4 - __builtin_popcount((unsigned)_mm256_movemask_pd(_mm256_castsi256_pd(gt)));
+    }
+    return s - 1;                                                                       // entry 0 (== 0) always counts
+}
+#endif
+
 extern "C" int gpc_ac_decode_h(const uint16_t *cdf, const uint8_t *in, int64_t in_len, int64_t n, int Lp, uint8_t *sym) {
-    GPC_REQUIRE(Lp >= 3 && sym, GPC_EINVAL, "bad argument");
-    BitReader br{in, in_len, 0, 0, 0};
-    u32 low = 0, high = 0xFFFFFFFFu, value = 0;
-    for (int i = 0; i < 32; ++i) value = (value << 1) | br.get();
+    GPC_REQUIRE(Lp >= 3 && Lp <= 17 && sym, GPC_EINVAL, "bad argument");
+    BitReservoir br{in, in_len, 0, 0, 0};
+    br.refill();
+    u32 low = 0, high = 0xFFFFFFFFu, value = br.take(32);
+    br.refill();
     const int top_sym = Lp - 2;
+#if defined(__x86_64__)
+    const bool avx2 = Lp == 17 && __builtin_cpu_supports("avx2");
+#else
+    const bool avx2 = false;
+#endif
     for (i64 i = 0; i < n; ++i) {
         const u16 *row = cdf + i * Lp;
         const u64 span = (u64)high - (u64)low + 1ull;
-        const u16 count = (u16)(((((u64)value - (u64)low + 1ull) << 16) - 1ull) / span);
+        const u64 num = ((((u64)value - (u64)low) + 1ull) << 16) - 1ull;        // < 2^49
         int s;
+        u64 p_lo, p_hi;
         if (Lp == 3) {
-            s = row[1] <= count;
+            const u64 p1 = (u64)row[1] * span;
+            s = p1 <= num;
+            p_lo = s ? p1 : 0;
+            p_hi = s ? (span << 16) : p1;
         } else {
-            int lo = 0, hi = top_sym + 1;
-            s = -1;
-            while (lo + 1 < hi) {
-                const int mid = (lo + hi) >> 1;
-                const u16 v = row[mid];
-                if (v < count) lo = mid; else if (v > count) hi = mid; else { s = mid; break; }
+#if defined(__x86_64__)
+            if (avx2) {
+                s = sym16_avx2(row, span, num);
+            } else
+#endif
+            {
+                s = 0;
+                for (int m = 1; m <= top_sym; ++m) s += (u64)row[m] * span <= num;
             }
-            if (s < 0) s = lo;
+            p_lo = (u64)row[s] * span;                                          // (re)computed: cheaper than reloading a vector store
+            p_hi = s == top_sym ? (span << 16) : (u64)row[s + 1] * span;       // top of the last symbol = 0x10000
         }
         sym[i] = (u8)s;
-        const u64 c_lo = row[s];
-        const u64 c_hi = s == top_sym ? 0x10000ull : (u64)row[s + 1];
+        high = (low - 1u) + (u32)(p_hi >> 16);
+        low = low + (u32)(p_lo >> 16);
+        for (;;) {
+            // shift out the whole common prefix of low/high (0..32 bits), branch-free
+            const u32 diff = low ^ high;
+            const int sh = diff ? __builtin_clz(diff) : 32;
+            if (br.have < 40) br.refill();
+            low = (u32)((u64)low << sh);
+            high = (u32)(((u64)high << sh) | ((1ull << sh) - 1ull));
+            value = (u32)((u64)value << sh) | br.take(sh);
+            if (!(low >= 0x40000000u && high < 0xC0000000u)) break;     // rare: interval straddles the midpoint
+            low = (low << 1) & 0x7FFFFFFFu;
+            high = (high << 1) | 0x80000001u;
+            value -= 0x40000000u;
+            value = (value << 1) | br.take(1);
+        }
+    }
+    return GPC_OK;
+}
+
+// Encoder fed with (c_low | c_high << 16) per symbol, c_high == 0 meaning 0x10000 (top symbol): what the fused head
+// kernel writes when it is given the symbol (gpc_head_cdf_sym) -- 4 bytes per row cross PCIe instead of 2*(A+1)+1.
+extern "C" int gpc_ac_encode_lohi_h(const uint32_t *lohi, int64_t n, uint8_t *out, int64_t cap, int64_t *out_len) {
+    GPC_REQUIRE(out && out_len, GPC_EINVAL, "bad argument");
+    FastWriter fw{out, cap, 0, 0, 0, false};
+    u32 low = 0, high = 0xFFFFFFFFu;
+    u64 pending = 0;
+    for (i64 i = 0; i < n; ++i) {
+        const u32 e = lohi[i];
+        const u64 c_lo = e & 0xFFFFu;
+        const u64 c_hi = (e >> 16) ? (u64)(e >> 16) : 0x10000ull;
+        const u64 span = (u64)high - (u64)low + 1ull;
         high = (low - 1u) + (u32)((span * c_hi) >> 16);
         low = low + (u32)((span * c_lo) >> 16);
         for (;;) {
-            if (low >= 0x80000000u || high < 0x80000000u) {
-                low <<= 1;
-                high = (high << 1) | 1u;
-                value = (value << 1) | br.get();
+            const u32 diff = low ^ high;
+            if (!(diff & 0x80000000u)) {
+                const int sh = diff ? __builtin_clz(diff) : 32;
+                const u32 first = low >> 31;
+                fw.put_bits(first, 1);
+                if (pending) { fw.put_run(first ^ 1u, pending); pending = 0; }
+                if (sh > 1) fw.put_bits(sh == 32 ? (low & 0x7FFFFFFFu) : ((low << 1) >> (32 - (sh - 1))), sh - 1);
+                if (sh == 32) { low = 0; high = 0xFFFFFFFFu; }
+                else { low <<= sh; high = (high << sh) | ((1u << sh) - 1u); }
             } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                ++pending;
                 low = (low << 1) & 0x7FFFFFFFu;
                 high = (high << 1) | 0x80000001u;
-                value -= 0x40000000u;
-                value = (value << 1) | br.get();
             } else {
                 break;
             }
         }
     }
+    ++pending;
+    const u32 last = low < 0x40000000u ? 0u : 1u;
+    fw.put_bits(last, 1);
+    fw.put_run(last ^ 1u, pending);
+    if (fw.n) fw.put_bits(0, 8 - fw.n);
+    *out_len = fw.len;
+    if (fw.overflow) { gpc_set_error("range coder output buffer too small"); return GPC_ENOSPC; }
     return GPC_OK;
 }

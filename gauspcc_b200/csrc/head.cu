@@ -90,7 +90,8 @@ template <int A>
 __global__ void __launch_bounds__(HD_ROWS) head_cdf_kernel(const float *__restrict__ f, i64 n, const float *__restrict__ W1,
                                                            const float *__restrict__ b1, const float *__restrict__ W2,
                                                            const float *__restrict__ b2, u16 *__restrict__ cdf,
-                                                           float *__restrict__ prob) {
+                                                           float *__restrict__ prob, const u8 *__restrict__ occ, int shift,
+                                                           u32 *__restrict__ lohi) {
     constexpr int Lp = A + 1;
     __shared__ float fs[HD_ROWS][GPC_C + 1];
     __shared__ __align__(16) float w1s[GPC_C][GPC_C];
@@ -141,31 +142,50 @@ __global__ void __launch_bounds__(HD_ROWS) head_cdf_kernel(const float *__restri
         const float scale = 65536.0f - (float)A;       // 2^16 - (Lp - 1), kit/op.py:67-70
         float c = 0.f;
         cs[tid * Lp] = 0;
+        const int my_sym = lohi ? (int)((occ[r0 + tid] >> shift) & (A - 1)) : -1;      // a-11 symbol split fused
+        u32 c_lo = 0, c_hi = 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             const float p = lg[a] / sum;
             if (prob) prob[(r0 + tid) * A + a] = p;
             c += p;                                     // sequential fp32 cumsum
             const float cc = fminf(fmaxf(c, 0.f), 1.f);
-            cs[tid * Lp + a + 1] = (u16)((u32)__float2int_rn(cc * scale) + (u32)(a + 1));   // int16 wrap == uint16 bits
+            const u16 q = (u16)((u32)__float2int_rn(cc * scale) + (u32)(a + 1));          // int16 wrap == uint16 bits
+            cs[tid * Lp + a + 1] = q;
+            if (a + 1 == my_sym) c_lo = q;
+            if (a == my_sym && a != A - 1) c_hi = q;    // top symbol: c_hi stays 0 == 0x10000
         }
+        if (lohi) lohi[r0 + tid] = c_lo | (c_hi << 16);
     }
     __syncthreads();
-    u16 *dst = cdf + r0 * Lp;
-    for (int i = tid; i < rows * Lp; i += HD_ROWS) dst[i] = cs[i];
+    if (cdf) {
+        u16 *dst = cdf + r0 * Lp;
+        for (int i = tid; i < rows * Lp; i += HD_ROWS) dst[i] = cs[i];
+    }
 }
 
-extern "C" int gpc_head_cdf(const float *f, int64_t n, const float *W1, const float *b1, const float *W2, const float *b2,
-                            int A, uint16_t *cdf, float *prob, void *stream) {
+static int head_launch(const float *f, int64_t n, const float *W1, const float *b1, const float *W2, const float *b2, int A,
+                       uint16_t *cdf, float *prob, const uint8_t *occ, int shift, uint32_t *lohi, void *stream) {
     if (n <= 0) return GPC_OK;
     cudaStream_t st = as_stream(stream);
     const unsigned grid = cdiv(n, HD_ROWS);
     switch (A) {
-        case 2: head_cdf_kernel<2><<<grid, HD_ROWS, 0, st>>>(f, n, W1, b1, W2, b2, cdf, prob); break;
-        case 4: head_cdf_kernel<4><<<grid, HD_ROWS, 0, st>>>(f, n, W1, b1, W2, b2, cdf, prob); break;
-        case 16: head_cdf_kernel<16><<<grid, HD_ROWS, 0, st>>>(f, n, W1, b1, W2, b2, cdf, prob); break;
+        case 2: head_cdf_kernel<2><<<grid, HD_ROWS, 0, st>>>(f, n, W1, b1, W2, b2, cdf, prob, occ, shift, lohi); break;
+        case 4: head_cdf_kernel<4><<<grid, HD_ROWS, 0, st>>>(f, n, W1, b1, W2, b2, cdf, prob, occ, shift, lohi); break;
+        case 16: head_cdf_kernel<16><<<grid, HD_ROWS, 0, st>>>(f, n, W1, b1, W2, b2, cdf, prob, occ, shift, lohi); break;
         default: gpc_set_error("unsupported alphabet %d (2, 4, 16)", A); return GPC_EINVAL;
     }
     GPC_LAUNCH_CHECK();
     return GPC_OK;
+}
+extern "C" int gpc_head_cdf(const float *f, int64_t n, const float *W1, const float *b1, const float *W2, const float *b2,
+                            int A, uint16_t *cdf, float *prob, void *stream) {
+    return head_launch(f, n, W1, b1, W2, b2, A, cdf, prob, nullptr, 0, nullptr, stream);
+}
+// encoder side: the symbol of this stage is (occ >> shift) & (A-1); writes lohi[o] = c_low | c_high << 16 (c_high == 0
+// means 0x10000) for gpc_ac_encode_lohi_h; cdf / prob may be NULL
+extern "C" int gpc_head_cdf_sym(const float *f, int64_t n, const float *W1, const float *b1, const float *W2, const float *b2,
+                                int A, const uint8_t *occ, int shift, uint32_t *lohi, uint16_t *cdf, float *prob, void *stream) {
+    GPC_REQUIRE(occ && lohi, GPC_EINVAL, "occ and lohi are required");
+    return head_launch(f, n, W1, b1, W2, b2, A, cdf, prob, occ, shift, lohi, stream);
 }

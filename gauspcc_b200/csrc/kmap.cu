@@ -102,7 +102,7 @@ extern "C" int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_
 constexpr int KP_THREADS = 256;
 
 __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_count_kernel(const i32 *__restrict__ map, i64 n, int tile_rows, int pad,
-                                                                     u32 *__restrict__ counts) {
+                                                                     u32 *__restrict__ counts, u32 *__restrict__ n_real) {
     __shared__ u32 cnt[GPC_K3 + 1];
     const i64 t = blockIdx.x;
     const i64 r0 = t * tile_rows;
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_count_kernel(const i32 
     __syncthreads();
     // pad > 1: every non-empty segment is rounded up to a multiple of `pad` entries (8-pair MMA tiles of one offset)
     for (int i = threadIdx.x; i <= GPC_K3; i += KP_THREADS) counts[t * (GPC_K3 + 1) + i] = (cnt[i] + pad - 1) / pad * pad;
+    if (threadIdx.x == 0) { u32 tot = 0; for (int i = 0; i < GPC_K3; ++i) tot += cnt[i]; atomicAdd(n_real, tot); }
 }
 
 __global__ void kmap_total_kernel(const u32 *__restrict__ seg, i64 m, u32 *__restrict__ n_pairs) { *n_pairs = seg[m]; }
@@ -162,11 +163,12 @@ __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_fill_kernel(const i32 *
 // kernels above spend their time in 125 x 3 __syncthreads with a quarter of the threads idle when tiles are small).
 template <int RPL>
 __global__ void __launch_bounds__(128) kmap_pairs_count_warp_kernel(const i32 *__restrict__ map, i64 n, i64 tiles, int pad,
-                                                                   u32 *__restrict__ counts) {
+                                                                   u32 *__restrict__ counts, u32 *__restrict__ n_real) {
     const int lane = threadIdx.x & 31;
     const i64 t = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= tiles) return;
     const i64 r0 = t * (32 * RPL);
+    u32 real = 0;
 #pragma unroll 5
     for (int k = 0; k < GPC_K3; ++k) {
         u32 c = 0;
@@ -176,10 +178,11 @@ __global__ void __launch_bounds__(128) kmap_pairs_count_warp_kernel(const i32 *_
             const bool v = r < n && map[(i64)k * n + r] >= 0;
             c += __popc(__ballot_sync(0xFFFFFFFFu, v));
         }
+        real += c;
         c = (c + pad - 1) / pad * pad;
         if (lane == 0) counts[t * (GPC_K3 + 1) + k] = c;
     }
-    if (lane == 0) counts[t * (GPC_K3 + 1) + GPC_K3] = 0;
+    if (lane == 0) { counts[t * (GPC_K3 + 1) + GPC_K3] = 0; atomicAdd(n_real, real); }
 }
 
 template <int RPL>
@@ -218,16 +221,17 @@ extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows
                                     void *ws, size_t ws_bytes, void *stream) {
     cudaStream_t st = as_stream(stream);
     GPC_REQUIRE(tile_rows > 0 && tile_rows <= 65536 && pad >= 1, GPC_EINVAL, "tile_rows must be in 1..65536, pad >= 1");
-    if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 4, st)); return GPC_OK; }
+    if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 8, st)); return GPC_OK; }
     GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_pairs_workspace_bytes(n, tile_rows), GPC_ENOSPC, "workspace too small");
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
     const i64 m = tiles * (GPC_K3 + 1);
     u32 *counts = (u32 *)ws;
     void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
-    if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts);
-    else if (tile_rows == 64) kmap_pairs_count_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts);
-    else if (tile_rows == 128) kmap_pairs_count_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts);
-    else kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts);
+    GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 8, st));      // n_pairs[0] = stream entries (padded), n_pairs[1] = true pairs
+    if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 64) kmap_pairs_count_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 128) kmap_pairs_count_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts, n_pairs + 1);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{counts};
     int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, seg, scan_ws, st);      // seg has m+1 entries

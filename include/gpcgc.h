@@ -116,7 +116,8 @@ int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, in
  * exclusive scan, *n_pairs device u32), then fill. */
 size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows);
 /* pad >= 1: every non-empty (tile, offset) segment is rounded up to a multiple of `pad` entries; the
- * padding entries of the combined stream are all-ones (INVALID).  *n_pairs counts padded entries. */
+ * padding entries of the combined stream are all-ones (INVALID).  n_pairs is a device u32[2]:
+ * [0] = stream entries (padded), [1] = true (row, neighbour) pairs. */
 int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows, int pad, uint32_t *seg, uint32_t *n_pairs,
                          void *ws, size_t ws_bytes, void *stream);
 /* fill writes the split arrays (pair_nbr/pair_row, may be NULL) and/or the combined stream
@@ -191,6 +192,11 @@ int gpc_add_ctx_embed(const float *u, const uint8_t *occ, int shift, const float
 /* cdf [n, A+1] uint16 (int16 bit pattern of kit/op.py:67-79); prob [n, A] optional (may be NULL) */
 int gpc_head_cdf(const float *f, int64_t n, const float *W1, const float *b1, const float *W2,
                  const float *b2, int A, uint16_t *cdf, float *prob, void *stream);
+/* encoder variant: symbol split (a-11) fused; lohi[o] = c_low | c_high << 16 of THE symbol (c_high == 0 means 0x10000),
+ * 4 bytes per row for the host coder instead of the whole CDF row; cdf / prob optional */
+int gpc_head_cdf_sym(const float *f, int64_t n, const float *W1, const float *b1, const float *W2,
+                     const float *b2, int A, const uint8_t *occ, int shift, uint32_t *lohi,
+                     uint16_t *cdf, float *prob, void *stream);
 /* a-11: symbol of stage i from the occupancy byte: sym = (occ >> shift) & mask */
 int gpc_split_symbol(const uint8_t *occ, int64_t n, int shift, int mask, uint8_t *sym, void *stream);
 /* decode: occ[o] |= sym[o] << shift */
@@ -201,6 +207,8 @@ int gpc_ac_encode_h(const uint16_t *cdf_h, const uint8_t *sym_h, int64_t n, int 
                     uint8_t *out_h, int64_t cap, int64_t *out_len_h);
 int gpc_ac_decode_h(const uint16_t *cdf_h, const uint8_t *in_h, int64_t in_len, int64_t n, int Lp,
                     uint8_t *sym_h);
+/* same bitstream as gpc_ac_encode_h, fed with the (c_low, c_high) words of gpc_head_cdf_sym */
+int gpc_ac_encode_lohi_h(const uint32_t *lohi_h, int64_t n, uint8_t *out_h, int64_t cap, int64_t *out_len_h);
 
 #ifdef __cplusplus
 }

@@ -157,3 +157,25 @@ def test_synthetic_clouds():
     assert np.array_equal(a, hac_like_cloud(20000, 0)) and not np.array_equal(a, hac_like_cloud(20000, 1))
     b = uniform_unique_cloud(5000, 1, extent_log2=10)
     assert np.unique(b, axis=0).shape[0] == 5000
+
+
+@pytest.mark.parametrize("A", [2, 4, 16])
+def test_lohi_encoder_same_bytes(A):
+    """gpc_ac_encode_lohi_h (fed with c_low | c_high << 16, 0 == 0x10000) produces the torchac-compatible bytes."""
+    lib = _lib.load()
+    rng = np.random.default_rng(A)
+    n = 20000
+    p = rng.dirichlet(np.full(A, 0.3), size=n).astype(np.float32)
+    p[:50] = 0; p[:50, A - 1] = 1.0
+    cdf = O.cdf_u16(p)
+    sym = rng.integers(0, A, n).astype(np.uint8)
+    sym[:5000] = np.array([rng.choice(A, p=r / r.sum()) for r in p[:5000].astype(np.float64)], dtype=np.uint8)
+    lo = cdf[np.arange(n), sym].astype(np.uint32)
+    hi = np.where(sym == A - 1, 0, cdf[np.arange(n), np.minimum(sym + 1, A)]).astype(np.uint32)
+    lohi = np.ascontiguousarray(lo | (hi << 16))
+    out = np.empty(4 * n + 64, np.uint8)
+    ln = C.c_int64(0)
+    assert lib.gpc_ac_encode_lohi_h(lohi.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), out.size, C.byref(ln)) == 0
+    ref = O.ac_encode(cdf, sym.astype(np.int16))
+    assert out[:ln.value].tobytes() == ref == _enc(lib, cdf, sym)
+    assert np.array_equal(_dec(lib, cdf, ref), sym)
