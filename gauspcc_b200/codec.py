@@ -136,6 +136,16 @@ class GausPcgcCodec:
         self._segments = []
         return ms
 
+    def _profile_events(self):
+        """timing events come from a pool that is created once: cudaEventCreate inside the timed region is not free"""
+        if not hasattr(self, "_ev_pool"):
+            self._ev_pool, self._ev_next = [], 0
+        if self._ev_next + 2 > len(self._ev_pool):
+            self._ev_pool += [torch.cuda.Event(enable_timing=True) for _ in range(4096)]
+        e0, e1 = self._ev_pool[self._ev_next], self._ev_pool[self._ev_next + 1]
+        self._ev_next += 2
+        return e0, e1
+
     def _call(self, name, *args):
         _lib.check(getattr(self.lib, name)(*args), name)
 
@@ -259,7 +269,7 @@ class GausPcgcCodec:
         n = x.shape[0]
         y = out if out is not None else self._empty((n, 32), torch.float32)
         if self.conv_profile is not None:
-            e0 = torch.cuda.Event(enable_timing=True)
+            e0, e1 = self._profile_events()
             e0.record(torch.cuda.current_stream(self.dev))
         wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
         if self.conv_variant >= 60:
@@ -284,7 +294,6 @@ class GausPcgcCodec:
             self._call("gpc_spconv_fwd", _ptr(x), _ptr(wt), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_row), n,
                        km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
         if self.conv_profile is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(self.dev))
             # per layer n*C*4*2 + pairs*8 + K^3*C^2*4 bytes and 2*pairs*C^2 FLOP
             self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
