@@ -93,7 +93,8 @@ class GausPcgcCodec:
         self.lib = _lib.load()
         self.dev = torch.device(device if device is not None else "cuda")
         self.w = weights
-        self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 40))
+        self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 42))
+        self.adaptive_tiles = os.environ.get("GPC_ADAPTIVE_TILES", "1") != "0" and tile_rows is None
         self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
@@ -223,6 +224,19 @@ class GausPcgcCodec:
         return ck, cp
 
     # ------------------------------------------------------------------ kernel map / conv
+    def _tile_rows_for(self, n: int) -> int:
+        """rows per warp of the conv: 64 on big levels (W^T reuse), fewer on the coarse levels so that they still fill the
+        148 SMs with warps (ncu launch list: the 7 levels below 81 K rows were 34 % of the conv time at a fixed 64)."""
+        if self.conv_variant != 42 or self.adaptive_tiles is False:
+            return self.tile_rows
+        if n >= 150_000:
+            return 64
+        if n >= 40_000:
+            return 32
+        if n >= 20_000:
+            return 16
+        return 8
+
     def build_kmap(self, keys: torch.Tensor, keep_dense: bool = False):
         n = keys.shape[0]
         cap = self.lib.gpc_hash_capacity(n)
@@ -245,7 +259,7 @@ class GausPcgcCodec:
             tl = self._empty((max(n_tiles, 1) * 8,), torch.int32)
             self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
             return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
-        tr = self.tile_rows
+        tr = self._tile_rows_for(n)
         tiles = (n + tr - 1) // tr
         seg = self._empty((tiles * 126 + 1,), torch.int32)
         cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)

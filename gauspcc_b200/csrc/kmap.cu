@@ -212,6 +212,48 @@ __global__ void __launch_bounds__(128) kmap_pairs_fill_warp_kernel(const i32 *__
     }
 }
 
+// ---- sub-warp tiles (tile_rows = 8 or 16): one warp covers 32 / TW tiles, each group of TW lanes is one tile.
+// Small tiles give the conv enough warps on the coarse octree levels (a few hundred to a few ten-thousand rows).
+template <int TW>
+__global__ void __launch_bounds__(128) kmap_pairs_count_sub_kernel(const i32 *__restrict__ map, i64 n, i64 tiles, int pad,
+                                                                  u32 *__restrict__ counts, u32 *__restrict__ n_real) {
+    constexpr int SUB = 32 / TW;
+    const int lane = threadIdx.x & 31, sub = lane / TW, rl = lane % TW;
+    const i64 t = ((i64)blockIdx.x * 4 + (threadIdx.x >> 5)) * SUB + sub;
+    const i64 r = t * TW + rl;
+    const bool live = t < tiles;
+    u32 real = 0;
+#pragma unroll 5
+    for (int k = 0; k < GPC_K3; ++k) {
+        const bool v = live && r < n && map[(i64)k * n + r] >= 0;
+        const u32 bits = (__ballot_sync(0xFFFFFFFFu, v) >> (TW * sub)) & ((1u << TW) - 1u);
+        const u32 c = __popc(bits);
+        real += c;
+        if (live && rl == 0) counts[t * (GPC_K3 + 1) + k] = (c + pad - 1) / pad * pad;
+    }
+    if (live && rl == 0) { counts[t * (GPC_K3 + 1) + GPC_K3] = 0; atomicAdd(n_real, real); }
+}
+template <int TW>
+__global__ void __launch_bounds__(128) kmap_pairs_fill_sub_kernel(const i32 *__restrict__ map, i64 n, i64 tiles,
+                                                                 const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr,
+                                                                 u16 *__restrict__ pair_row, u64 *__restrict__ pairs) {
+    constexpr int SUB = 32 / TW;
+    const int lane = threadIdx.x & 31, sub = lane / TW, rl = lane % TW;
+    const i64 t = ((i64)blockIdx.x * 4 + (threadIdx.x >> 5)) * SUB + sub;
+    const i64 r = t * TW + rl;
+    const bool live = t < tiles;
+#pragma unroll 5
+    for (int k = 0; k < GPC_K3; ++k) {
+        const i32 nb = (live && r < n) ? map[(i64)k * n + r] : -1;
+        const u32 bits = (__ballot_sync(0xFFFFFFFFu, nb >= 0) >> (TW * sub)) & ((1u << TW) - 1u);
+        if (nb >= 0) {
+            const u32 q = seg[t * (GPC_K3 + 1) + k] + __popc(bits & ((1u << rl) - 1u));
+            if (pair_nbr) { pair_nbr[q] = (u32)nb; pair_row[q] = (u16)rl; }
+            if (pairs) pairs[q] = (u64)(u32)nb | ((u64)(u32)rl << 32) | ((u64)(u32)k << 48);
+        }
+    }
+}
+
 extern "C" size_t gpc_kmap_pairs_workspace_bytes(int64_t n, int tile_rows) {
     const i64 tiles = n > 0 ? (n + tile_rows - 1) / tile_rows : 1;
     const i64 m = tiles * (GPC_K3 + 1);
@@ -228,7 +270,9 @@ extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows
     u32 *counts = (u32 *)ws;
     void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
     GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 8, st));      // n_pairs[0] = stream entries (padded), n_pairs[1] = true pairs
-    if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    if (tile_rows == 8) kmap_pairs_count_sub_kernel<8><<<cdiv(tiles, 16), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 16) kmap_pairs_count_sub_kernel<16><<<cdiv(tiles, 8), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
     else if (tile_rows == 64) kmap_pairs_count_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
     else if (tile_rows == 128) kmap_pairs_count_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
     else kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts, n_pairs + 1);
@@ -247,7 +291,9 @@ extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows,
     if (pairs && n_entries > 0) GPC_CUDA_CHECK(cudaMemsetAsync(pairs, 0xFF, (size_t)n_entries * 8, as_stream(stream)));
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
     cudaStream_t st = as_stream(stream);
-    if (tile_rows == 32) kmap_pairs_fill_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    if (tile_rows == 8) kmap_pairs_fill_sub_kernel<8><<<cdiv(tiles, 16), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 16) kmap_pairs_fill_sub_kernel<16><<<cdiv(tiles, 8), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 32) kmap_pairs_fill_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
     else if (tile_rows == 64) kmap_pairs_fill_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
     else if (tile_rows == 128) kmap_pairs_fill_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
     else kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, seg, pair_nbr, pair_row, pairs);

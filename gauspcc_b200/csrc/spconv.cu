@@ -1225,6 +1225,14 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
     } else if (variant == 41) {
         if (tile_rows == 64) return launch_spconv_v6<64, 12>(x, Wa, seg, pairs, n, residual, flags, y, st);
         if (tile_rows == 128) return launch_spconv_v6<128, 12>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 42) {
+        if (tile_rows == 8) return launch_spconv_v6<8, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 16) return launch_spconv_v6<16, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 32) return launch_spconv_v6<32, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 64) return launch_spconv_v6<64, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 128) return launch_spconv_v6<128, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 43) {
+        if (tile_rows == 64) return launch_spconv_v6<64, 3>(x, Wa, seg, pairs, n, residual, flags, y, st);
     }
     gpc_set_error("unsupported conv v6 variant %d / tile_rows %d", variant, tile_rows);
     return GPC_EINVAL;
