@@ -6,13 +6,17 @@
 // fresh SparseTensor (pcc_utils.py:100,108,124,132,140); here it is built ONCE per coordinate set and
 // shared by all convs on that set.
 //
-// Table: open addressing, linear probing, 16-byte slots {u64 key, u32 row, u32 pad} so a probe is one
-// 128-bit load; capacity = power of two >= 2n (the whole table of a 1M-row level is 32 MB: L2 resident).
+// Table: open addressing, linear probing, 16-byte slots {u64 block key, u32 base row, u32 mask} (one slot per x-block
+// of 8 voxels) so a probe is one 128-bit load; capacity = power of two >= 2n (32 MB for a 1M-row level: L2 resident).
 // Dense map is OFFSET-MAJOR [125][n] (coalesced over rows); offset index x-fastest
 // k = ((dz+2)*5 + (dy+2))*5 + (dx+2).  The conv consumes per-tile pair lists grouped by offset.
 #include "common.cuh"
 
-struct __align__(16) HashSlot { u64 key; u32 row; u32 pad; };
+// One slot describes an x-BLOCK of 8 voxels: key = voxel key >> 3 (= z, y, x>>3), `row` = row of the block's first
+// voxel, `mask` = which of the 8 x positions are occupied.  Rows are sorted with x fastest, so a block's voxels are
+// consecutive rows and row(x) = base + popcount(mask below x).  One 16-byte probe answers 8 positions: the 5 x-offsets
+// of a (dz,dy) line fall into at most 2 blocks -> ~37 probes per row instead of 124.
+struct __align__(16) HashSlot { u64 key; u32 row; u32 mask; };
 
 __device__ __forceinline__ u32 hash_key(u64 k) {      // murmur3 fmix64
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
@@ -25,28 +29,44 @@ extern "C" int64_t gpc_hash_capacity(int64_t n) {
     return cap;
 }
 
+// keys sorted ascending, unique.  The first row of every x-block inserts the block.
 __global__ void hash_insert_kernel(const u64 *__restrict__ keys, i64 n, HashSlot *table, u32 mask) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 key = keys[i];
-    u32 slot = hash_key(key) & mask;
+    const u64 bk = key >> 3;
+    if (i > 0 && (keys[i - 1] >> 3) == bk) return;
+    u32 m = 1u << (u32)(key & 7);
+    for (i64 j = i + 1; j < n && j < i + 8; ++j) {
+        const u64 kj = keys[j];
+        if ((kj >> 3) != bk) break;
+        m |= 1u << (u32)(kj & 7);
+    }
+    u32 slot = hash_key(bk) & mask;
     while (true) {
         unsigned long long prev = atomicCAS((unsigned long long *)&table[slot].key, (unsigned long long)GPC_EMPTY_KEY,
-                                            (unsigned long long)key);
-        if (prev == GPC_EMPTY_KEY || prev == key) { table[slot].row = (u32)i; return; }
+                                            (unsigned long long)bk);
+        if (prev == GPC_EMPTY_KEY || prev == bk) { table[slot].row = (u32)i; table[slot].mask = m; return; }
         slot = (slot + 1) & mask;
     }
 }
 
-__device__ __forceinline__ i32 hash_find(const HashSlot *__restrict__ table, u32 mask, u64 key) {
-    u32 slot = hash_key(key) & mask;
+// -> (base row, occupancy mask) of block bk, or mask 0 when absent
+__device__ __forceinline__ uint2 hash_find_block(const HashSlot *__restrict__ table, u32 mask, u64 bk) {
+    u32 slot = hash_key(bk) & mask;
     while (true) {
         const uint4 raw = __ldg((const uint4 *)&table[slot]);
         const u64 k = ((u64)raw.y << 32) | raw.x;
-        if (k == key) return (i32)raw.z;
-        if (k == GPC_EMPTY_KEY) return -1;
+        if (k == bk) return make_uint2(raw.z, raw.w);
+        if (k == GPC_EMPTY_KEY) return make_uint2(0u, 0u);
         slot = (slot + 1) & mask;
     }
+}
+__device__ __forceinline__ i32 block_row(uint2 b, u32 bit) {
+    return ((b.y >> bit) & 1u) ? (i32)(b.x + __popc(b.y & ((1u << bit) - 1u))) : -1;
+}
+__device__ __forceinline__ i32 hash_find(const HashSlot *__restrict__ table, u32 mask, u64 key) {
+    return block_row(hash_find_block(table, mask, key >> 3), (u32)(key & 7));
 }
 
 extern "C" int gpc_hash_build(const uint64_t *keys, int64_t n, void *table, int64_t capacity, void *stream) {
@@ -72,25 +92,29 @@ extern "C" int gpc_hash_lookup(const void *table, int64_t capacity, const uint64
     return GPC_OK;
 }
 
-// one thread per (offset k, row o); blockIdx.y = k so writes are coalesced over rows
+// one thread per (row o, line (dz,dy)); blockIdx.y = line, so every one of the 5 output planes is written coalesced
 __global__ void kmap_dense_kernel(const HashSlot *__restrict__ table, u32 mask, const u64 *__restrict__ keys, i64 n,
                                   i32 *__restrict__ map) {
-    const int k = blockIdx.y;
+    const int line = blockIdx.y;                      // (dz+2)*5 + (dy+2)
     i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n) return;
-    const int dx = k % 5 - 2, dy = (k / 5) % 5 - 2, dz = k / 25 - 2;
-    i32 r;
-    if (k == 62) r = (i32)o;
-    else {
-        const i64 delta = (i64)dx + ((i64)dy << 21) + ((i64)dz << 42);   // fields never under/overflow: |c| <= 2^20-16
-        r = hash_find(table, mask, (u64)((i64)keys[o] + delta));
+    const int dy = line % 5 - 2, dz = line / 5 - 2;
+    // fields never under/overflow: |c| <= 2^20 - 16
+    const u64 k0 = (u64)((i64)keys[o] + ((i64)dy << 21) + ((i64)dz << 42) - 2);       // voxel at dx = -2
+    const u64 b0 = k0 >> 3, b1 = (k0 + 4) >> 3;
+    const uint2 e0 = hash_find_block(table, mask, b0);
+    const uint2 e1 = b1 != b0 ? hash_find_block(table, mask, b1) : e0;
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+        const u64 kk = k0 + dx;
+        const i32 r = block_row((kk >> 3) == b0 ? e0 : e1, (u32)(kk & 7));
+        map[(i64)(line * 5 + dx) * n + o] = r;
     }
-    map[(i64)k * n + o] = r;
 }
 extern "C" int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n, int32_t *map,
                               void *stream) {
     if (n <= 0) return GPC_OK;
-    dim3 grid(cdiv(n, 256), GPC_K3);
+    dim3 grid(cdiv(n, 256), 25);
     kmap_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>((const HashSlot *)table, (u32)(capacity - 1), keys, n, map);
     GPC_LAUNCH_CHECK();
     return GPC_OK;

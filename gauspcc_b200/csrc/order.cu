@@ -151,16 +151,29 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const u64 *__restri
     hist[(i64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// Stable scatter of one tile.  Ranks come from warp-level match_any (no atomics on the output order); the tile is first
+// re-ordered by digit in shared memory, so that the global writes are contiguous runs per digit (a 4096-key tile over
+// 256 digits = 128-byte runs) instead of one 8 + 4 byte record per thread at a random address.
+struct RsSmem {
+    u64 keys[RS_TILE];
+    u32 vals[RS_TILE];
+    u32 whist[RS_WARPS][256];
+    u32 dstart[256];
+    u32 gbase[256];
+};
+
 template <bool XF, bool IOTA>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                                                                 u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, i64 n,
                                                                 gpc_key_xform xf, int shift,
                                                                 const u32 *__restrict__ hist_scanned, int nblocks) {
-    __shared__ u32 whist[RS_WARPS][256];
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    RsSmem &s = *reinterpret_cast<RsSmem *>(rs_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s.whist[0][0])[i] = 0;
     __syncthreads();
-    const i64 wbase = (i64)blockIdx.x * RS_TILE + (i64)warp * (32 * RS_IPT);
+    const i64 tbase = (i64)blockIdx.x * RS_TILE;
+    const i64 wbase = tbase + (i64)warp * (32 * RS_IPT);
     u64 k[RS_IPT];
     u32 v[RS_IPT], rk[RS_IPT];
 #pragma unroll
@@ -177,27 +190,48 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
         u32 d = valid ? rs_digit<XF>(k[r], xf, shift) : (0x100u | (u32)lane);
         u32 peers = __match_any_sync(0xFFFFFFFFu, d);
         u32 lower = __popc(peers & lt_mask);
-        u32 prev = valid ? whist[warp][d] : 0u;
+        u32 prev = valid ? s.whist[warp][d] : 0u;
         __syncwarp();
-        if (valid && lower == 0) whist[warp][d] = prev + __popc(peers);
+        if (valid && lower == 0) s.whist[warp][d] = prev + __popc(peers);
         __syncwarp();
         rk[r] = prev + lower;
     }
     __syncthreads();
-    {
+    {   // per digit: exclusive scan across warps, then exclusive scan across digits (tile-local start of each digit)
         const int d = tid;
-        u32 off = hist_scanned[(i64)d * nblocks + blockIdx.x];
+        u32 off = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) { u32 t = whist[w][d]; whist[w][d] = off; off += t; }
+        for (int w = 0; w < RS_WARPS; ++w) { u32 t = s.whist[w][d]; s.whist[w][d] = off; off += t; }
+        // off = number of keys of digit d in this tile; block-wide exclusive scan over the 256 digits
+        u32 incl = off;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        s.gbase[d] = incl;                       // temporarily: inclusive within the warp's 32 digits
+        __syncthreads();
+        u32 warp_off = 0;
+        for (int w = 0; w < warp; ++w) warp_off += s.gbase[w * 32 + 31];
+        const u32 start = warp_off + incl - off;
+        __syncthreads();
+        s.dstart[d] = start;
+        s.gbase[d] = hist_scanned[(i64)d * nblocks + blockIdx.x] - start;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_IPT; ++r) {
         if ((wbase + r * 32 + lane) < n) {
-            u32 pos = whist[warp][rs_digit<XF>(k[r], xf, shift)] + rk[r];
-            keys_out[pos] = k[r];
-            vals_out[pos] = v[r];
+            const u32 d = rs_digit<XF>(k[r], xf, shift);
+            const u32 lp = s.dstart[d] + s.whist[warp][d] + rk[r];
+            s.keys[lp] = k[r];
+            s.vals[lp] = v[r];
         }
+    }
+    __syncthreads();
+    const int count = (int)min((i64)RS_TILE, n - tbase);
+    for (int p = tid; p < count; p += RS_THREADS) {
+        const u64 key = s.keys[p];
+        const u32 pos = s.gbase[rs_digit<XF>(key, xf, shift)] + (u32)p;
+        keys_out[pos] = key;
+        vals_out[pos] = s.vals[p];
     }
 }
 
@@ -232,6 +266,12 @@ static int sort_pairs_impl(const u64 *keys_in, const u32 *vals_in, u64 *keys_out
     if (n <= 0) return GPC_OK;
     SortWs L = sort_ws_layout(ws, n);
     GPC_REQUIRE(ws && ws_bytes >= L.total, GPC_ENOSPC, "sort workspace too small");
+    static bool configured = false;
+    if (!configured) {
+        GPC_CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<XF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        GPC_CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<XF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        configured = true;
+    }
     const int P = (total_bits + 7) / 8;
     const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
     const int passes = P == 0 ? 1 : P;     // all keys equal: one pass over a zero digit = stable identity
@@ -249,9 +289,9 @@ static int sort_pairs_impl(const u64 *keys_in, const u32 *vals_in, u64 *keys_out
         int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, (i64)256 * nblocks, L.hist_scanned, L.scan_ws, st);
         if (rc) return rc;
         if (p == 0 && src_v == nullptr)
-            rs_scatter_kernel<XF, true><<<nblocks, RS_THREADS, 0, st>>>(src_k, nullptr, dst_k, dst_v, n, xf, shift, L.hist_scanned, nblocks);
+            rs_scatter_kernel<XF, true><<<nblocks, RS_THREADS, sizeof(RsSmem), st>>>(src_k, nullptr, dst_k, dst_v, n, xf, shift, L.hist_scanned, nblocks);
         else
-            rs_scatter_kernel<XF, false><<<nblocks, RS_THREADS, 0, st>>>(src_k, src_v, dst_k, dst_v, n, xf, shift, L.hist_scanned, nblocks);
+            rs_scatter_kernel<XF, false><<<nblocks, RS_THREADS, sizeof(RsSmem), st>>>(src_k, src_v, dst_k, dst_v, n, xf, shift, L.hist_scanned, nblocks);
         GPC_LAUNCH_CHECK();
         src_k = dst_k; src_v = dst_v;
     }

@@ -104,6 +104,7 @@ int gpc_expand_leaves_f32(const uint64_t *parent_keys, const uint8_t *parent_occ
 
 /* ---- kernel maps (torchsparse hashmap kmap; pcc_utils.py:50-52) ---- */
 int64_t gpc_hash_capacity(int64_t n);                      /* slots; table bytes = 16 * slots */
+/* keys must be sorted ascending and unique (one slot per x-block of 8 voxels is inserted by the block's first row) */
 int gpc_hash_build(const uint64_t *keys, int64_t n, void *table, int64_t capacity, void *stream);
 int gpc_hash_lookup(const void *table, int64_t capacity, const uint64_t *query, int64_t n,
                     int32_t *rows, void *stream);
