@@ -63,6 +63,8 @@ SIGNATURES = {
     "gpc_kmap_rt8_fill": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_spconv_fwd_v7": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_spconv_fwd_v8": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    "gpc_spconv_pack_weights_umma": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "gpc_spconv_fwd_v9": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),

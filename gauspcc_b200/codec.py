@@ -77,6 +77,9 @@ class DeviceWeights:
         self.convs_frag = torch.empty_like(self.convs)                               # [18,125,2,2,2,32] uint4: mma A fragments of W^T
         _lib.check(lib.gpc_spconv_pack_weights_frag(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_frag),
                                                     C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_frag")
+        self.convs_umma = torch.empty_like(self.convs)                               # [18,125,2,2 KB]: UMMA canonical images of W[k] hi / lo
+        _lib.check(lib.gpc_spconv_pack_weights_umma(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_umma),
+                                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_umma")
         self.convs_bf16 = torch.empty_like(self.convs)                               # [18,125,2,8,32] x (4 x bf16): hi / lo halves
         _lib.check(lib.gpc_spconv_pack_weights_bf16(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_bf16),
                                                     C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_bf16")
@@ -95,7 +98,7 @@ class GausPcgcCodec:
         self.w = weights
         self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 42))
         self.adaptive_tiles = os.environ.get("GPC_ADAPTIVE_TILES", "1") != "0" and tile_rows is None
-        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))
+        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 256 if self.conv_variant >= 70 else (64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256))))
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -265,7 +268,7 @@ class GausPcgcCodec:
         cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
         ws_b = self.lib.gpc_kmap_pairs_workspace_bytes(n, tr)
         ws = self._ws(ws_b)
-        pad = 8 if (self.conv_variant >= 40 and not keep_dense) else 1
+        pad = 8 if (40 <= self.conv_variant < 70 and not keep_dense) else 1
         self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
         n_pairs, n_real = (int(v) for v in cnt.tolist())
         split = self.conv_variant < 10 or keep_dense
@@ -286,7 +289,10 @@ class GausPcgcCodec:
             e0, e1 = self._profile_events()
             e0.record(torch.cuda.current_stream(self.dev))
         wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
-        if self.conv_variant >= 60:
+        if self.conv_variant >= 70:
+            self._call("gpc_spconv_fwd_v9", _ptr(x), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+        elif self.conv_variant >= 60:
             self._call("gpc_spconv_fwd_v8", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
                        _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
         elif self.conv_variant >= 50:

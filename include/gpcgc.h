@@ -179,6 +179,14 @@ int gpc_spconv_fwd_v8(const float *x, const void *Wa, const uint32_t *seg, const
                       int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                       void *stream);
 
+/* v9 (variant 70): tcgen05.mma (kind::f16, bf16 hi/lo split, fp32 accumulators in TMEM) over chunks of <= 128 pairs of one
+ * offset; CTA tiles of `tile_rows` output rows (pair stream with pad = 1); Wc from gpc_spconv_pack_weights_umma
+ * ([125][2][2 KB] canonical K-major no-swizzle images of W[k] hi / lo) */
+int gpc_spconv_pack_weights_umma(const float *W, int n_kernels, void *Wc, void *stream);
+int gpc_spconv_fwd_v9(const float *x, const void *Wc, const uint32_t *seg, const uint64_t *pairs,
+                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                      void *stream);
+
 /* ---- a-6/a-9/a-12: embeddings ---- */
 /* out[o,:] = table[idx[o],:]  (prior_embedding, network_ue_4stage_conv.py:15) */
 int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *stream);
