@@ -49,6 +49,7 @@ class KMap:
     tiles: Optional[torch.Tensor] = None
     n_tiles: int = 0
     n_real: int = 0                           # true (row, neighbour) pairs -- filled in bench profiling mode only
+    cta_rows: int = 0                         # > 0: tcgen05 conv (v10); tile_rows == cta_rows / 4 (the quarters of a CTA tile)
 
 
 @dataclass
@@ -98,7 +99,9 @@ class GausPcgcCodec:
         self.w = weights
         self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 42))
         self.adaptive_tiles = os.environ.get("GPC_ADAPTIVE_TILES", "1") != "0" and tile_rows is None
-        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 256 if self.conv_variant >= 70 else (64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256))))
+        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 512 if self.conv_variant >= 80 else (256 if self.conv_variant >= 70 else (64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))))
+        # levels below this many rows keep the mma.sync conv (v6, small per-warp tiles fill the SMs); above: tcgen05 (v10)
+        self.umma_min_rows = int(os.environ.get("GPC_UMMA_MIN_ROWS", 60_000))
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -230,7 +233,9 @@ class GausPcgcCodec:
     def _tile_rows_for(self, n: int) -> int:
         """rows per warp of the conv: 64 on big levels (W^T reuse), fewer on the coarse levels so that they still fill the
         148 SMs with warps (ncu launch list: the 7 levels below 81 K rows were 34 % of the conv time at a fixed 64)."""
-        if self.conv_variant != 42 or self.adaptive_tiles is False:
+        if self.conv_variant >= 80 and not self.adaptive_tiles:
+            return 64                      # self.tile_rows is the CTA tile of the tcgen05 levels
+        if self.conv_variant not in (42, 80) or self.adaptive_tiles is False:
             return self.tile_rows
         if n >= 150_000:
             return 64
@@ -239,6 +244,15 @@ class GausPcgcCodec:
         if n >= 20_000:
             return 16
         return 8
+
+    def _cta_rows_for(self, n: int) -> int:
+        """rows per CTA of the tcgen05 conv (0 = this level runs the mma.sync conv): one CTA per SM, so a level needs
+        a few hundred tiles before the big tile (denser 128-pair chunks per offset) pays."""
+        if self.conv_variant < 80 or n < self.umma_min_rows:
+            return 0
+        if not self.adaptive_tiles:
+            return self.tile_rows
+        return 512
 
     def build_kmap(self, keys: torch.Tensor, keep_dense: bool = False):
         n = keys.shape[0]
@@ -262,13 +276,14 @@ class GausPcgcCodec:
             tl = self._empty((max(n_tiles, 1) * 8,), torch.int32)
             self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
             return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
-        tr = self._tile_rows_for(n)
+        cta_rows = self._cta_rows_for(n) if not keep_dense else 0
+        tr = cta_rows // 4 if cta_rows else self._tile_rows_for(n)
         tiles = (n + tr - 1) // tr
         seg = self._empty((tiles * 126 + 1,), torch.int32)
         cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
         ws_b = self.lib.gpc_kmap_pairs_workspace_bytes(n, tr)
         ws = self._ws(ws_b)
-        pad = 8 if (40 <= self.conv_variant < 70 and not keep_dense) else 1
+        pad = 8 if ((40 <= self.conv_variant < 70 or self.conv_variant >= 80) and not keep_dense and not cta_rows) else 1
         self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
         n_pairs, n_real = (int(v) for v in cnt.tolist())
         split = self.conv_variant < 10 or keep_dense
@@ -279,17 +294,44 @@ class GausPcgcCodec:
                    n_pairs if pad > 1 else 0, self._stream())
         km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
         km.n_real = n_real
+        km.cta_rows = cta_rows
         return (km, dense) if keep_dense else km
 
+    def split_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """fp32 rows [n,32] -> split rows (int32 [n,32]: 16 words of bf16x2 hi | 16 words of bf16x2 lo)."""
+        xs = self._empty(x.shape, torch.int32)
+        self._call("gpc_rows_split", _ptr(x), x.shape[0], _ptr(xs), self._stream())
+        return xs
+
     def conv(self, x: torch.Tensor, widx: int, km: KMap, residual: Optional[torch.Tensor] = None, relu: bool = False,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+             out: Optional[torch.Tensor] = None, fmt: str = "f32"):
+        """One sparse conv.  Activations are fp32 rows (float32 tensors) or split rows (int32 tensors, tcgen05 levels
+        only); fmt = "f32" | "split" | "both" selects what is written ("both" returns (f32, split))."""
         n = x.shape[0]
+        if km.cta_rows:
+            xs = x if x.dtype == torch.int32 else self.split_rows(x)
+            y = (out if out is not None else self._empty((n, 32), torch.float32)) if fmt in ("f32", "both") else None
+            ys = self._empty((n, 32), torch.int32) if fmt in ("split", "both") else None
+            if self.conv_profile is not None:
+                e0, e1 = self._profile_events()
+                e0.record(torch.cuda.current_stream(self.dev))
+            flags = (1 if relu else 0) | (2 if (residual is not None and residual.dtype == torch.int32) else 0)
+            self._call("gpc_spconv_fwd_v10", _ptr(xs), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.cta_rows,
+                       _ptr(residual), flags, _ptr(y), _ptr(ys), self.conv_variant, self._stream())
+            if self.conv_profile is not None:
+                e1.record(torch.cuda.current_stream(self.dev))
+                self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
+            return y if fmt == "f32" else (ys if fmt == "split" else (y, ys))
+        assert fmt == "f32" and x.dtype == torch.float32
         y = out if out is not None else self._empty((n, 32), torch.float32)
         if self.conv_profile is not None:
             e0, e1 = self._profile_events()
             e0.record(torch.cuda.current_stream(self.dev))
         wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
-        if self.conv_variant >= 70:
+        if self.conv_variant >= 80:
+            self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), 1 if relu else 0, _ptr(y), 42, self._stream())
+        elif self.conv_variant >= 70:
             self._call("gpc_spconv_fwd_v9", _ptr(x), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
                        _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
         elif self.conv_variant >= 60:
@@ -319,8 +361,14 @@ class GausPcgcCodec:
             self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
         return y
 
-    def res_stack(self, x: torch.Tensor, ids, km: KMap) -> torch.Tensor:
+    def res_stack(self, x: torch.Tensor, ids, km: KMap, final: str = "f32"):
         """Conv3d, ReLU, ResNet, ResNet (network_ue_4stage_conv.py:17-22; ResNet kit/nn.py:18-22)."""
+        if km.cta_rows:            # tcgen05 level: everything between the first and the last conv stays in split rows
+            x = self.conv(x, ids[0], km, relu=True, fmt="split")
+            t = self.conv(x, ids[1], km, relu=True, fmt="split")
+            x = self.conv(t, ids[2], km, residual=x, relu=True, fmt="split")
+            t = self.conv(x, ids[3], km, relu=True, fmt="split")
+            return self.conv(t, ids[4], km, residual=x, relu=True, fmt=final)
         x = self.conv(x, ids[0], km, relu=True)
         for a, b in ((ids[1], ids[2]), (ids[3], ids[4])):
             t = self.conv(x, a, km, relu=True)
@@ -339,7 +387,8 @@ class GausPcgcCodec:
         self._call("gpc_gather_parent_add_octant", _ptr(f), _ptr(cp), _ptr(ck), n_child, _ptr(self.w.target_emb), _ptr(u0),
                    self._stream())
         child = Level(ck, None, n_child, self.build_kmap(ck))
-        u = self.res_stack(u0, W.TARGET_CONVS, child.kmap)
+        # tcgen05 level: u is needed as fp32 rows (context embeddings) and as split rows (stage 0 conv input)
+        u = self.res_stack(u0, W.TARGET_CONVS, child.kmap, final="both" if child.kmap.cta_rows else "f32")
         return child, u
 
     def stage_cdf(self, u: torch.Tensor, occ_partial: Optional[torch.Tensor], i: int, km: KMap, cdf_out: Optional[torch.Tensor],
@@ -347,15 +396,16 @@ class GausPcgcCodec:
         """stage i: (+ context embedding) -> spatial_conv_s{i} -> pred_head_s{i} -> uint16 CDF rows.
         Encoder: lohi_out given => occ_partial is the TRUE occupancy, the stage's symbol is split off inside the head kernel
         and only (c_low, c_high) of that symbol is written (4 B per row for the host coder)."""
+        u, u_split = u if isinstance(u, tuple) else (u, None)
         n = u.shape[0]
         if i == 0:
-            f = u
+            f = u_split if u_split is not None else u
         else:
             f = self._empty((n, 32), torch.float32)
             self._call("gpc_add_ctx_embed", _ptr(u), _ptr(occ_partial), CTX_SHIFT[i], _ptr(self.w.stage_emb[i]), n, _ptr(f),
                        self._stream())
         c0, c1 = W.stage_convs(i)
-        t = self.conv(f, c0, km, relu=True)
+        t = self.conv(f, c0, km, relu=True, fmt="split" if km.cta_rows else "f32")
         t = self.conv(t, c1, km)
         w1, b1, w2, b2 = self.w.head[i]
         if lohi_out is not None:

@@ -77,6 +77,29 @@ __host__ __device__ __forceinline__ u64 key_compact(u64 k, gpc_key_xform t) {
     return (z << t.sz) | (y << t.sy) | x;
 }
 
+// ---------------------------------------------------------------- bf16 hi / lo split of fp32 (x = hi + lo + O(2^-17 x))
+__device__ __forceinline__ u32 pack_bf16x2(float lo, float hi) {
+    u32 r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // upper half <- first source
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) {                       // round-to-nearest-even to bf16, as fp32
+    u32 u = __float_as_uint(v);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return __uint_as_float(u & 0xFFFF0000u);
+}
+// (p0, p1) -> packed bf16x2 words: hi = bf16(p), lo = bf16(p - hi); p0 in the low half (lower address)
+__device__ __forceinline__ void split_bf16(float p0, float p1, u32 &hi, u32 &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float p0h = __uint_as_float(hi << 16), p1h = __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(p1 - p1h), "f"(p0 - p0h));
+}
+// the inverse for "split rows" (see spconv_umma.cu): two channels from one hi word and one lo word
+__device__ __forceinline__ float2 join_bf16(u32 hi, u32 lo) {
+    return make_float2(__uint_as_float(hi << 16) + __uint_as_float(lo << 16),
+                       __uint_as_float(hi & 0xFFFF0000u) + __uint_as_float(lo & 0xFFFF0000u));
+}
+
 // ---------------------------------------------------------------- generic device-wide exclusive scan
 // T needs operator+ and a zero(); LoadOp(i) produces element i.  Three phases per level:
 //   scan_tiles: per-tile exclusive scan + tile total; (recursive) scan of tile totals; add_offsets.

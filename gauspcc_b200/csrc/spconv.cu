@@ -546,16 +546,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const u32 (&a)[4],
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ u32 pack_bf16x2(float lo, float hi) {
-    u32 r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // upper half <- first source
-    return r;
-}
-__device__ __forceinline__ float bf16_round(float v) {                       // round-to-nearest-even to bf16, as fp32
-    u32 u = __float_as_uint(v);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return __uint_as_float(u & 0xFFFF0000u);
-}
 
 // W [n_kernels*125][32 ci][32 co] fp32 -> Wb [n_kernels*125][2 (hi,lo)][8 q][32 co] of 4 x bf16 (channels 4q..4q+3)
 __global__ void pack_weights_bf16_kernel(const float *__restrict__ W, u64 *__restrict__ Wb, int n_kernels) {
@@ -839,11 +829,6 @@ struct Sc5Smem {
     u32 sb[GPC_K3 + 3];          // their stream begin (relative); sb[nseg] = total
 };
 
-__device__ __forceinline__ void split_bf16(float p0, float p1, u32 &hi, u32 &lo) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
-    const float p0h = __uint_as_float(hi << 16), p1h = __uint_as_float(hi & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(p1 - p1h), "f"(p0 - p0h));
-}
 __device__ __forceinline__ void mma_bf16_a4(float (&d)[4], const uint4 &a, u32 b0, u32 b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -1664,215 +1649,6 @@ extern "C" int gpc_spconv_fwd_v8(const float *x, const void *Wa, const uint32_t 
     return GPC_EINVAL;
 }
 
-
-// =====================================================================================================
-// v9: tcgen05 / TMEM contraction.  One CTA (4 warps) owns TM consecutive output rows with fp32 accumulators in
-// shared memory; the tile's pair stream (sorted by offset, row) is cut into chunks of <= 128 pairs of ONE offset.
-// Per chunk: thread i gathers input row i, splits it into bf16 hi / lo and stores both into UMMA canonical
-// K-major (no-swizzle) operand tiles; W[k] hi / lo come as a pre-packed canonical image; ONE thread issues
-//     D[128 pairs x 32 co] (TMEM, fp32)  =  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi     (6 x tcgen05.mma kind::f16, K = 16)
-// and commits to an mbarrier; every warp then reads its 32 TMEM lanes (tcgen05.ld 32x32b.x32: one full output row
-// per thread) and adds it into the accumulator row of its pair.  Operands never pass through the register file
-// as MMA fragments (v6: 4 KB of W^T fragments per offset change per warp, 12 HMMA + 24 conversions per 8 pairs);
-// here each thread does one row gather + one row scatter-add per pair and the tensor core does the rest.
-// Chunks are processed in stream order with a CTA barrier between them: fixed accumulation order per output row.
-// =====================================================================================================
-constexpr int SC9_ACC = 36;
-constexpr u32 SC9_IDESC = (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ |
-                          ((32u >> 3) << 17) /* N = 32 */ | ((128u >> 4) << 24) /* M = 128 */;   // A, B K-major, dense
-
-// canonical K-major no-swizzle tile: element (row r, col c) of a [rows x 32] bf16 tile lives at
-//   (r / 8) * 512 + (c / 8) * 128 + (r % 8) * 16 + (c % 8) * 2      (8 x 16-byte core matrices, LBO = 128, SBO = 512)
-__host__ __device__ __forceinline__ u32 umma_off(int r, int c) { return (u32)((r >> 3) * 512 + (c >> 3) * 128 + (r & 7) * 16 + (c & 7) * 2); }
-
-// W [n_kernels*125][32 ci][32 co] fp32 -> Wc [n_kernels*125][2 (hi, lo)][2 KB canonical image of B[n = co][c = ci]]
-__global__ void pack_weights_umma_kernel(const float *__restrict__ W, u16 *__restrict__ Wc, int n_kernels) {
-    i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (i64)n_kernels * GPC_K3 * GPC_C * GPC_C) return;
-    const int co = (int)(g & 31), ci = (int)((g >> 5) & 31);
-    const i64 k = g >> 10;
-    const float w = W[k * 1024 + ci * 32 + co];
-    const float w1 = bf16_round(w), w2 = bf16_round(w - w1);
-    u16 *dst = Wc + k * 2048;                       // 4 KB per offset = 2048 u16
-    dst[umma_off(co, ci) / 2] = (u16)(__float_as_uint(w1) >> 16);
-    dst[1024 + umma_off(co, ci) / 2] = (u16)(__float_as_uint(w2) >> 16);
-}
-extern "C" int gpc_spconv_pack_weights_umma(const float *W, int n_kernels, void *Wc, void *stream) {
-    const i64 total = (i64)n_kernels * GPC_K3 * GPC_C * GPC_C;
-    pack_weights_umma_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(W, (u16 *)Wc, n_kernels);
-    GPC_LAUNCH_CHECK();
-    return GPC_OK;
-}
-
-__device__ __forceinline__ u64 umma_desc(u32 smem_addr) {      // K-major, SWIZZLE_NONE, LBO = 128 B, SBO = 512 B
-    return (u64)((smem_addr >> 4) & 0x3FFFu) | ((u64)(128u >> 4) << 16) | ((u64)(512u >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void umma_bf16(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-    // bounded: a mis-programmed MMA / commit must fault the launch (trap), never hang the GPU
-    for (u32 spins = 0; spins < (1u << 24); ++spins) {
-        u32 done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-
-template <int TM>
-struct Sc9Smem {
-    float acc[TM][SC9_ACC];
-    __align__(128) unsigned char a_hi[8192];
-    __align__(128) unsigned char a_lo[8192];
-    __align__(128) unsigned char b[4096];          // hi image then lo image
-    __align__(8) u64 mbar;
-    u32 tmem_base;
-    u32 seg[GPC_K3 + 1];
-};
-
-template <int TM>
-__global__ void __launch_bounds__(128) spconv_fwd_v9_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wc,
-                                                            const u32 *__restrict__ seg_g, const u64 *__restrict__ pairs, i64 n,
-                                                            const float *__restrict__ residual, int flags, float *__restrict__ y) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Sc9Smem<TM> &s = *reinterpret_cast<Sc9Smem<TM> *>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const i64 t = blockIdx.x;
-    const i64 r0 = t * TM;
-    const int rows = (int)min((i64)TM, n - r0);
-
-    for (int i = tid; i <= GPC_K3; i += 128) s.seg[i] = seg_g[t * (GPC_K3 + 1) + i];
-    for (int i = tid; i < TM * SC9_ACC / 4; i += 128) reinterpret_cast<float4 *>(&s.acc[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const u32 bar = (u32)__cvta_generic_to_shared(&s.mbar);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        const u32 dst = (u32)__cvta_generic_to_shared(&s.tmem_base);
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(dst) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const u32 tmem_d = s.tmem_base;
-    const u32 a_hi = (u32)__cvta_generic_to_shared(s.a_hi), a_lo = (u32)__cvta_generic_to_shared(s.a_lo);
-    const u32 b_hi = (u32)__cvta_generic_to_shared(s.b), b_lo = b_hi + 2048;
-    const u32 my_a = (u32)((tid >> 3) * 512 + (tid & 7) * 16);          // row `tid` of the operand tile, column group 0
-
-    u32 parity = 0;
-    int cur_k = -1;
-    const u32 p_end = s.seg[GPC_K3];
-    int k = 0;
-    for (u32 p = s.seg[0]; p < p_end;) {
-        while (p >= s.seg[k + 1]) ++k;
-        const int cnt = (int)min(128u, s.seg[k + 1] - p);
-        // ---- gather + split: thread i <-> pair i of the chunk
-        u32 my_row = 0xFFFFu;
-        if (tid < cnt) {
-            const u64 e = __ldg(pairs + p + tid);
-            my_row = (u32)(e >> 32) & 0xFFFFu;
-            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)(u32)e * GPC_C);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                                 // 8 channels per 16-byte core-matrix row
-                const float4 v0 = __ldg(src + 2 * j), v1 = __ldg(src + 2 * j + 1);
-                u32 h0, l0, h1, l1, h2, l2, h3, l3;
-                split_bf16(v0.x, v0.y, h0, l0); split_bf16(v0.z, v0.w, h1, l1);
-                split_bf16(v1.x, v1.y, h2, l2); split_bf16(v1.z, v1.w, h3, l3);
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi + my_a + j * 128), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo + my_a + j * 128), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
-            }
-        }
-        if (k != cur_k) {                                                  // block-uniform: 4 KB canonical image of W[k]
-            cur_k = k;
-            const uint4 *wsrc = Wc + (size_t)k * 256;
-            reinterpret_cast<uint4 *>(s.b)[tid] = __ldg(wsrc + tid);
-            reinterpret_cast<uint4 *>(s.b)[tid + 128] = __ldg(wsrc + tid + 128);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem_d, umma_desc(a_lo + ks * 256), umma_desc(b_hi + ks * 256), SC9_IDESC, ks);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem_d, umma_desc(a_hi + ks * 256), umma_desc(b_lo + ks * 256), SC9_IDESC, 1u);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) umma_bf16(tmem_d, umma_desc(a_hi + ks * 256), umma_desc(b_hi + ks * 256), SC9_IDESC, 1u);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: thread i holds row i of D (32 fp32) -> add into the accumulator row of its pair
-        u32 d[32];
-        const u32 taddr = tmem_d + ((u32)(warp * 32) << 16);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
-                       "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
-                       "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
-                       "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
-                     : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (my_row != 0xFFFFu) {
-            float4 *a = reinterpret_cast<float4 *>(&s.acc[my_row][0]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 v = a[j];
-                v.x += __uint_as_float(d[4 * j]); v.y += __uint_as_float(d[4 * j + 1]);
-                v.z += __uint_as_float(d[4 * j + 2]); v.w += __uint_as_float(d[4 * j + 3]);
-                a[j] = v;
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                       // operand tiles, TMEM and the accumulator rows are free for the next chunk
-        p += cnt;
-    }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_d) : "memory");
-    const bool relu = (flags & GPC_CONV_RELU) != 0;
-    const int lane = tid & 31;
-    for (int r = warp; r < rows; r += 4) {
-        float v = s.acc[r][lane];
-        if (residual) v += __ldg(residual + (r0 + r) * GPC_C + lane);
-        if (relu) v = fmaxf(v, 0.f);
-        y[(r0 + r) * GPC_C + lane] = v;
-    }
-}
-
-template <int TM>
-static int launch_spconv_v9(const float *x, const void *Wc, const u32 *seg, const u64 *pairs, i64 n, const float *residual,
-                            int flags, float *y, cudaStream_t st) {
-    static bool configured = false;
-    const size_t smem = sizeof(Sc9Smem<TM>) + 128;
-    if (!configured) {
-        GPC_CUDA_CHECK(cudaFuncSetAttribute(spconv_fwd_v9_kernel<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const i64 tiles = (n + TM - 1) / TM;
-    spconv_fwd_v9_kernel<TM><<<(unsigned)tiles, 128, smem, st>>>(x, (const uint4 *)Wc, seg, pairs, n, residual, flags, y);
-    GPC_LAUNCH_CHECK();
-    return GPC_OK;
-}
-
-// variant 70: Wc from gpc_spconv_pack_weights_umma; pair stream with pad = 1 and tile_rows = TM
-extern "C" int gpc_spconv_fwd_v9(const float *x, const void *Wc, const uint32_t *seg, const uint64_t *pairs, int64_t n,
-                                 int tile_rows, const float *residual, int flags, float *y, int variant, void *stream) {
-    if (n <= 0) return GPC_OK;
-    GPC_REQUIRE(x != y, GPC_EINVAL, "conv is out of place (rows are gathered from x while y is written)");
-    cudaStream_t st = as_stream(stream);
-    if (variant == 70) {
-        if (tile_rows == 128) return launch_spconv_v9<128>(x, Wc, seg, pairs, n, residual, flags, y, st);
-        if (tile_rows == 256) return launch_spconv_v9<256>(x, Wc, seg, pairs, n, residual, flags, y, st);
-        if (tile_rows == 512) return launch_spconv_v9<512>(x, Wc, seg, pairs, n, residual, flags, y, st);
-    }
-    gpc_set_error("unsupported conv v9 variant %d / tile_rows %d", variant, tile_rows);
-    return GPC_EINVAL;
-}
 
 // variant: 0 = v1 (unpipelined, W in reference layout), 1.. = v2 configurations (W packed by gpc_spconv_pack_weights)
 extern "C" int gpc_spconv_fwd(const float *x, const float *W, const uint32_t *seg, const uint32_t *pair_nbr,

@@ -187,6 +187,22 @@ int gpc_spconv_fwd_v9(const float *x, const void *Wc, const uint32_t *seg, const
                       int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                       void *stream);
 
+/* "split rows": an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits) -- the
+ * operand format of the tcgen05 conv: a gathered row is copied straight into the tensor-core operand tile */
+int gpc_rows_split(const float *x, int64_t n, void *xs, void *stream);
+int gpc_rows_join(const void *xs, int64_t n, float *x, void *stream);
+
+/* v10 (variant 80): warp-specialised tcgen05 pipeline (gather warps -> cp.async ring -> tcgen05.mma -> TMEM ->
+ * scatter-add warps).  xs = split rows; CTA tiles of cta_rows (256 / 512 / 1024) output rows = 4 quarters, pair stream built
+ * with tile_rows = cta_rows / 4 and pad = 1; Wc from gpc_spconv_pack_weights_umma.  Outputs: y (fp32 rows) and / or ys
+ * (split rows), either may be NULL.  flags: GPC_CONV_RELU, GPC_CONV_RES_SPLIT (residual points to split rows). */
+#define GPC_CONV_RES_SPLIT 2
+int gpc_spconv_fwd_v10(const void *xs, const void *Wc, const uint32_t *seg, const uint64_t *pairs, int64_t n,
+                       int cta_rows, const void *residual, int flags, float *y, void *ys, int variant, void *stream);
+
+/* variant 89 = v10 with per-role cycle counters; out_h = host u64[16] (layout: spconv_umma.cu), reset != 0 clears them */
+int gpc_debug_conv_profile(unsigned long long *out_h, int reset);
+
 /* ---- a-6/a-9/a-12: embeddings ---- */
 /* out[o,:] = table[idx[o],:]  (prior_embedding, network_ue_4stage_conv.py:15) */
 int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *stream);

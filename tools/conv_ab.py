@@ -32,20 +32,32 @@ def main():
             codec.conv_profile = None
             g = torch.Generator(device=dev).manual_seed(li)
             x = torch.randn((lv.n, 32), device=dev, generator=g)
-            y = codec.conv(x, 3, km, relu=True)
+            xin = codec.split_rows(x) if km.cta_rows else x
+            y = codec.conv(xin, 3, km, relu=True)
             torch.cuda.synchronize()
             if li not in ref:
                 ref[li] = y.clone()
             err = float((y - ref[li]).abs().max())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
+            if variant == 89:
+                codec.lib.gpc_debug_conv_profile(None, 1)
             e0.record()
             for _ in range(reps):
-                codec.conv(x, 3, km, relu=True, out=y)
+                codec.conv(xin, 3, km, relu=True, out=y)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             tot_ms += ms; tot_pairs += km.n_real
             clk = ms * 1e-3 * 1.9e9 * 148 / max(km.n_real, 1)
+            if variant == 89 and km.cta_rows:
+                import ctypes
+                buf = (ctypes.c_uint64 * 16)()
+                codec.lib.gpc_debug_conv_profile(ctypes.cast(buf, ctypes.c_void_p), 1)
+                ch = max(buf[9], 1)
+                names = ["g.empty", "g.issue", "g.wait", "m.full", "m.dempty", "m.issue", "e.dfull", "e.ld", "e.rmw"]
+                ctas = reps * ((lv.n + km.cta_rows - 1) // km.cta_rows)
+                print(f"   prof n={lv.n}: chunks/cta={ch / ctas:.0f} " + " ".join(f"{nm}={buf[i] / ch:.0f}" for i, nm in enumerate(names))
+                      + f" | per cta: total={buf[10] / ctas:.0f} setup={buf[11] / ctas:.0f} writeout={buf[12] / ctas:.0f}")
             line.append(f"n={lv.n} tiles={km.n_tiles} p/r={km.n_real / lv.n:.1f} {ms:.3f}ms {clk:.1f}clk/pair err={err:.1e}")
         print(f"variant {variant} tile {tr}: total {tot_ms:.2f} ms, {tot_ms * 1e-3 * 1.9e9 * 148 / tot_pairs:.1f} clk/pair/SM")
         for l in line:
