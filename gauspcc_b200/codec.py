@@ -99,9 +99,9 @@ class GausPcgcCodec:
         self.w = weights
         self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 42))
         self.adaptive_tiles = os.environ.get("GPC_ADAPTIVE_TILES", "1") != "0" and tile_rows is None
-        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 512 if self.conv_variant >= 80 else (256 if self.conv_variant >= 70 else (64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))))
+        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", (1024 if self.conv_variant >= 90 else 512) if self.conv_variant >= 80 else (256 if self.conv_variant >= 70 else (64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))))
         # levels below this many rows keep the mma.sync conv (v6, small per-warp tiles fill the SMs); above: tcgen05 (v10)
-        self.umma_min_rows = int(os.environ.get("GPC_UMMA_MIN_ROWS", 60_000))
+        self.umma_min_rows = int(os.environ.get("GPC_UMMA_MIN_ROWS", 150_000))
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -235,7 +235,7 @@ class GausPcgcCodec:
         148 SMs with warps (ncu launch list: the 7 levels below 81 K rows were 34 % of the conv time at a fixed 64)."""
         if self.conv_variant >= 80 and not self.adaptive_tiles:
             return 64                      # self.tile_rows is the CTA tile of the tcgen05 levels
-        if self.conv_variant not in (42, 80) or self.adaptive_tiles is False:
+        if (self.conv_variant != 42 and self.conv_variant < 80) or self.adaptive_tiles is False:
             return self.tile_rows
         if n >= 150_000:
             return 64
@@ -252,7 +252,7 @@ class GausPcgcCodec:
             return 0
         if not self.adaptive_tiles:
             return self.tile_rows
-        return 512
+        return 1024 if self.conv_variant >= 90 else 512
 
     def build_kmap(self, keys: torch.Tensor, keep_dense: bool = False):
         n = keys.shape[0]

@@ -206,6 +206,62 @@ def test_sparse_conv(env, n, ext):
     assert np.allclose(y3, 2 * y, rtol=1e-6, atol=1e-6)
 
 
+@pytest.fixture(scope="module")
+def env_umma(env):
+    """A second codec whose levels ALL run the tcgen05 conv (variant 90, split rows), whatever their size."""
+    from gauspcc_b200.codec import GausPcgcCodec
+    codec = GausPcgcCodec(env["codec"].w, env["dev"])
+    codec.conv_variant = 90
+    codec.umma_min_rows = 1
+    codec.tile_rows = 1024
+    return dict(env, codec=codec)
+
+
+@pytest.mark.parametrize("n,ext,cta_rows", [(30000, 16, 1024), (30000, 16, 512), (2000, 6, 1024), (1025, 5, 1024), (77, 4, 512)])
+def test_sparse_conv_tcgen05(env_umma, n, ext, cta_rows):
+    """tcgen05 / TMEM conv over split rows against the fp32 oracle conv: fp32 and split outputs, residual in both formats."""
+    from gauspcc_b200.codec import _ptr
+    from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
+    from oracle import oracle as O
+    codec, w = env_umma["codec"], env_umma["w"]
+    codec.adaptive_tiles, codec.tile_rows = False, cta_rows
+    try:
+        xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
+        xyz = xyz[O.sort_zyx_perm(xyz)]
+        keys, _ = _keys_of(codec, xyz)
+        km = codec.build_kmap(keys)
+        assert km.cta_rows == cta_rows and km.tile_rows == cta_rows // 4
+        ref_km = O.kmap(xyz, 5)
+        rng = np.random.default_rng(0)
+        x = rng.normal(size=(n, 32)).astype(np.float32)
+        res = rng.normal(size=(n, 32)).astype(np.float32)
+        xd, rd = torch.tensor(x, device=codec.dev), torch.tensor(res, device=codec.dev)
+        ref = O.conv(x, w["target_resnet.2.conv1.kernel"], ref_km)
+        scale = max(np.abs(ref).max(), 1.0)
+        y = codec.conv(xd, 7, km).cpu().numpy()
+        assert np.abs(y - ref).max() <= 3e-5 * scale
+        # split-row input / output / residual: same numbers up to the 2^-17 relative rounding of a split row
+        xs, rs = codec.split_rows(xd), codec.split_rows(rd)
+        y2f, y2s = codec.conv(xs, 7, km, residual=rs, relu=True, fmt="both")
+        y2 = y2f.cpu().numpy()
+        assert np.abs(y2 - np.maximum(ref + res, 0)).max() <= 6e-5 * scale
+        joined = torch.empty_like(y2f)
+        codec._call("gpc_rows_join", _ptr(y2s), n, _ptr(joined), codec._stream())
+        assert np.abs(joined.cpu().numpy() - y2).max() <= 2e-5 * scale
+        y3 = codec.conv(xs, 7, km, residual=rd, relu=True).cpu().numpy()          # fp32 residual
+        assert np.abs(y3 - y2).max() <= 3e-5 * scale
+        # deterministic: bit-identical on a second launch (encoder / decoder CDF identity depends on it)
+        assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)
+    finally:
+        codec.adaptive_tiles, codec.tile_rows = True, 1024
+
+
+@pytest.mark.parametrize("n,seed,ext", [(20000, 1, 16), (2500, 5, 12)])
+def test_codec_tcgen05_vs_oracle(env_umma, n, seed, ext):
+    """the whole codec with every level on the tcgen05 conv: same bars as test_codec_vs_oracle"""
+    test_codec_vs_oracle(env_umma, n, seed, ext)
+
+
 @pytest.mark.parametrize("i", [0, 1, 2, 3])
 def test_head_cdf(env, i):
     from gauspcc_b200.codec import _ptr

@@ -40,7 +40,7 @@ def main():
             err = float((y - ref[li]).abs().max())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
-            if variant == 89:
+            if variant in (89, 99):
                 codec.lib.gpc_debug_conv_profile(None, 1)
             e0.record()
             for _ in range(reps):
@@ -49,15 +49,16 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             tot_ms += ms; tot_pairs += km.n_real
             clk = ms * 1e-3 * 1.9e9 * 148 / max(km.n_real, 1)
-            if variant == 89 and km.cta_rows:
+            if variant in (89, 99) and km.cta_rows:
                 import ctypes
-                buf = (ctypes.c_uint64 * 16)()
+                buf = (ctypes.c_uint64 * 32)()
                 codec.lib.gpc_debug_conv_profile(ctypes.cast(buf, ctypes.c_void_p), 1)
                 ch = max(buf[9], 1)
                 names = ["g.empty", "g.issue", "g.wait", "m.full", "m.dempty", "m.issue", "e.dfull", "e.ld", "e.rmw"]
                 ctas = reps * ((lv.n + km.cta_rows - 1) // km.cta_rows)
                 print(f"   prof n={lv.n}: chunks/cta={ch / ctas:.0f} " + " ".join(f"{nm}={buf[i] / ch:.0f}" for i, nm in enumerate(names))
-                      + f" | per cta: total={buf[10] / ctas:.0f} setup={buf[11] / ctas:.0f} writeout={buf[12] / ctas:.0f}")
+                      + f" | per cta: total={buf[10] / ctas:.0f} setup={buf[11] / ctas:.0f} writeout={buf[12] / ctas:.0f}"
+                      + " | fine " + " ".join(f"{buf[16 + i] / ch:.0f}" for i in range(10)))
             line.append(f"n={lv.n} tiles={km.n_tiles} p/r={km.n_real / lv.n:.1f} {ms:.3f}ms {clk:.1f}clk/pair err={err:.1e}")
         print(f"variant {variant} tile {tr}: total {tot_ms:.2f} ms, {tot_ms * 1e-3 * 1.9e9 * 148 / tot_pairs:.1f} clk/pair/SM")
         for l in line:
