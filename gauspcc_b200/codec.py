@@ -49,7 +49,9 @@ class KMap:
     tiles: Optional[torch.Tensor] = None
     n_tiles: int = 0
     n_real: int = 0                           # true (row, neighbour) pairs -- filled in bench profiling mode only
-    cta_rows: int = 0                         # > 0: tcgen05 conv (v10); tile_rows == cta_rows / 4 (the quarters of a CTA tile)
+    cta_rows: int = 0                         # > 0: tcgen05 conv; tile_rows == cta_rows / 4 (the quarters of a CTA tile)
+    _fill: object = None
+    v6_variant: int = 42                      # mma.sync conv: 42 = one warp per tile, 45 / 46 / 47 = offsets split over 2 / 8 / 16 warps
 
 
 @dataclass
@@ -97,11 +99,18 @@ class GausPcgcCodec:
         self.lib = _lib.load()
         self.dev = torch.device(device if device is not None else "cuda")
         self.w = weights
+        # 42 (default): the mma.sync conv (v6) on every level, tile shape by level size (_v6_config)
+        # 100: tcgen05 conv (spconv_tc.cu) on the big dense levels, v6 elsewhere; 101: same with the role profile.  Parity-green and
+        #      at par with v6 on the dense levels, but not faster end to end yet (profiles/r01_conv_tcgen05.md), hence opt-in
+        # other values < 70: one of the earlier kernels on every level (kept for A/B, tools/conv_ab.py)
         self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 42))
         self.adaptive_tiles = os.environ.get("GPC_ADAPTIVE_TILES", "1") != "0" and tile_rows is None
-        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", (1024 if self.conv_variant >= 90 else 512) if self.conv_variant >= 80 else (256 if self.conv_variant >= 70 else (64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))))
-        # levels below this many rows keep the mma.sync conv (v6, small per-warp tiles fill the SMs); above: tcgen05 (v10)
-        self.umma_min_rows = int(os.environ.get("GPC_UMMA_MIN_ROWS", 150_000))
+        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))
+        # a level runs the tcgen05 conv when it has enough rows to fill 148 one-per-SM CTAs a few times over AND enough pairs per
+        # row for the 128-row MMA chunks of one offset to be reasonably full (tools/conv_ab.py: break-even near 5 pairs per row)
+        self.tc_min_rows = int(os.environ.get("GPC_TC_MIN_ROWS", 150_000))
+        self.tc_min_density = float(os.environ.get("GPC_TC_MIN_DENSITY", 5.0))
+        self.tc_cta_rows = int(os.environ.get("GPC_TC_CTA_ROWS", 1024))
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -230,29 +239,41 @@ class GausPcgcCodec:
         return ck, cp
 
     # ------------------------------------------------------------------ kernel map / conv
-    def _tile_rows_for(self, n: int) -> int:
-        """rows per warp of the conv: 64 on big levels (W^T reuse), fewer on the coarse levels so that they still fill the
-        148 SMs with warps (ncu launch list: the 7 levels below 81 K rows were 34 % of the conv time at a fixed 64)."""
-        if self.conv_variant >= 80 and not self.adaptive_tiles:
-            return 64                      # self.tile_rows is the CTA tile of the tcgen05 levels
-        if (self.conv_variant != 42 and self.conv_variant < 80) or self.adaptive_tiles is False:
-            return self.tile_rows
-        if n >= 150_000:
-            return 64
-        if n >= 40_000:
-            return 32
-        if n >= 20_000:
-            return 16
-        return 8
-
-    def _cta_rows_for(self, n: int) -> int:
-        """rows per CTA of the tcgen05 conv (0 = this level runs the mma.sync conv): one CTA per SM, so a level needs
-        a few hundred tiles before the big tile (denser 128-pair chunks per offset) pays."""
-        if self.conv_variant < 80 or n < self.umma_min_rows:
-            return 0
+    def _v6_config(self, n: int) -> Tuple[int, int]:
+        """(rows per CTA, kernel variant) of the mma.sync conv for a level of n rows (tools/conv_ab.py, AB_MIN_ROWS=50):
+        64 rows per warp on big levels (W^T reuse); fewer rows on the coarse levels so that they still fill the 148 SMs; on the
+        coarsest levels the 125 offsets of a tile are additionally split over 2 / 8 / 16 warps (variants 45 / 46 / 47): those
+        launches are bound by one warp's chain of dependent 8-pair tiles, ~63 us each before, 15-30 us now."""
+        if self.conv_variant < 100 and (self.conv_variant != 42 or not self.adaptive_tiles):
+            return self.tile_rows, self.conv_variant
         if not self.adaptive_tiles:
-            return self.tile_rows
-        return 1024 if self.conv_variant >= 90 else 512
+            return 64, 42
+        if n >= 150_000:
+            return 64, 42
+        if n >= 40_000:
+            return 32, 45
+        if n >= 20_000:
+            return 16, 42
+        if n >= 1_500:
+            return 16, 46
+        return 8, 47
+
+    def _pair_stream(self, dense: torch.Tensor, n: int, tr: int, pad: int, split: bool) -> KMap:
+        tiles = (n + tr - 1) // tr
+        seg = self._empty((tiles * 126 + 1,), torch.int32)
+        cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        ws_b = self.lib.gpc_kmap_pairs_workspace_bytes(n, tr)
+        ws = self._ws(ws_b)
+        self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
+        n_pairs, n_real = (int(v) for v in cnt.tolist())
+        pair_nbr = self._empty((max(n_pairs, 1),), torch.int32) if split else None
+        pair_row = self._empty((max(n_pairs, 1),), torch.int16) if split else None
+        pairs = self._empty((max(n_pairs, 1),), torch.int64) if self.conv_variant >= 10 else None
+        km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
+        km.n_real = n_real
+        km._fill = lambda: self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), _ptr(pairs),
+                                      n_pairs if pad > 1 else 0, self._stream())
+        return km
 
     def build_kmap(self, keys: torch.Tensor, keep_dense: bool = False):
         n = keys.shape[0]
@@ -276,25 +297,20 @@ class GausPcgcCodec:
             tl = self._empty((max(n_tiles, 1) * 8,), torch.int32)
             self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
             return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
-        cta_rows = self._cta_rows_for(n) if not keep_dense else 0
-        tr = cta_rows // 4 if cta_rows else self._tile_rows_for(n)
-        tiles = (n + tr - 1) // tr
-        seg = self._empty((tiles * 126 + 1,), torch.int32)
-        cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
-        ws_b = self.lib.gpc_kmap_pairs_workspace_bytes(n, tr)
-        ws = self._ws(ws_b)
-        pad = 8 if ((40 <= self.conv_variant < 70 or self.conv_variant >= 80) and not keep_dense and not cta_rows) else 1
-        self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
-        n_pairs, n_real = (int(v) for v in cnt.tolist())
-        split = self.conv_variant < 10 or keep_dense
-        pair_nbr = self._empty((max(n_pairs, 1),), torch.int32) if split else None
-        pair_row = self._empty((max(n_pairs, 1),), torch.int16) if split else None
-        pairs = self._empty((max(n_pairs, 1),), torch.int64) if self.conv_variant >= 10 else None
-        self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), _ptr(pairs),
-                   n_pairs if pad > 1 else 0, self._stream())
-        km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
-        km.n_real = n_real
-        km.cta_rows = cta_rows
+        km = None
+        if self.conv_variant >= 100 and not keep_dense and n >= self.tc_min_rows:
+            km = self._pair_stream(dense, n, self.tc_cta_rows // 4, 1, False)        # quarters of a tcgen05 CTA tile
+            if km.n_real >= self.tc_min_density * n:
+                km.cta_rows = self.tc_cta_rows
+            else:
+                km = None                                                            # too sparse: count again with the warp tiling
+        if km is None:
+            pad = 8 if ((40 <= self.conv_variant < 70 or self.conv_variant >= 100) and not keep_dense) else 1
+            tr, v6v = self._v6_config(n)
+            km = self._pair_stream(dense, n, tr, pad, self.conv_variant < 10 or keep_dense)
+            km.v6_variant = v6v
+        km._fill()
+        km._fill = None
         return (km, dense) if keep_dense else km
 
     def split_rows(self, x: torch.Tensor) -> torch.Tensor:
@@ -316,8 +332,8 @@ class GausPcgcCodec:
                 e0, e1 = self._profile_events()
                 e0.record(torch.cuda.current_stream(self.dev))
             flags = (1 if relu else 0) | (2 if (residual is not None and residual.dtype == torch.int32) else 0)
-            self._call("gpc_spconv_fwd_v10", _ptr(xs), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.cta_rows,
-                       _ptr(residual), flags, _ptr(y), _ptr(ys), self.conv_variant, self._stream())
+            self._call("gpc_spconv_fwd_tc", _ptr(xs), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.cta_rows,
+                       _ptr(residual), flags, _ptr(y), _ptr(ys), 1 if self.conv_variant == 101 else 0, self._stream())
             if self.conv_profile is not None:
                 e1.record(torch.cuda.current_stream(self.dev))
                 self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
@@ -328,12 +344,9 @@ class GausPcgcCodec:
             e0, e1 = self._profile_events()
             e0.record(torch.cuda.current_stream(self.dev))
         wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
-        if self.conv_variant >= 80:
+        if self.conv_variant >= 100 or self.conv_variant == 42:
             self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), 42, self._stream())
-        elif self.conv_variant >= 70:
-            self._call("gpc_spconv_fwd_v9", _ptr(x), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+                       _ptr(residual), 1 if relu else 0, _ptr(y), km.v6_variant, self._stream())
         elif self.conv_variant >= 60:
             self._call("gpc_spconv_fwd_v8", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
                        _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())

@@ -1032,19 +1032,25 @@ struct Sc6Smem {
     u32 rowk[D][12];              // [0..7] row of each pair in the tile (0xFFFF = padding), [8] = offset k
 };
 
-template <int TW, int D>
-__global__ void __launch_bounds__(32) spconv_fwd_v6_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
-                                                           const u32 *__restrict__ seg_g, const u64 *__restrict__ pairs, i64 n,
-                                                           const float *__restrict__ residual, int flags, float *__restrict__ y) {
+// G > 1 ("split offsets"): the CTA has G warps on the SAME TW rows; warp w contracts the offsets [125 w / G, 125 (w+1) / G) into its
+// own accumulators and the partial sums are added in warp order at the end (still one fixed summation order per row).  The coarse
+// octree levels have a few hundred to a few thousand rows with 35-70 neighbours each: one warp per 8 rows walked ~100 dependent
+// 8-pair tiles and every such launch took ~70 us whatever its size (launch list, profiles/r01_step_breakdown.md).
+template <int TW, int D, int G>
+__global__ void __launch_bounds__(32 * G) spconv_fwd_v6_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
+                                                               const u32 *__restrict__ seg_g, const u64 *__restrict__ pairs, i64 n,
+                                                               const float *__restrict__ residual, int flags, float *__restrict__ y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Sc6Smem<TW, D> &s = *reinterpret_cast<Sc6Smem<TW, D> *>(smem_raw);
-    const int lane = threadIdx.x;
+    const int wid = G > 1 ? (int)(threadIdx.x >> 5) : 0;
+    Sc6Smem<TW, D> &s = reinterpret_cast<Sc6Smem<TW, D> *>(smem_raw)[wid];
+    const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const i64 st = blockIdx.x;
     const i64 r0 = st * TW;
     const int rows = (int)min((i64)TW, n - r0);
-    const u32 p_begin = __ldg(seg_g + st * (GPC_K3 + 1));
-    const int ntiles = (int)((__ldg(seg_g + st * (GPC_K3 + 1) + GPC_K3) - p_begin) >> 3);
+    const int kb = GPC_K3 * wid / G, ke = GPC_K3 * (wid + 1) / G;
+    const u32 p_begin = __ldg(seg_g + st * (GPC_K3 + 1) + kb);
+    const int ntiles = (int)((__ldg(seg_g + st * (GPC_K3 + 1) + ke) - p_begin) >> 3);
     const u64 *tile_base = pairs + p_begin;
 
     for (int i = lane; i < TW * SC6_ACC / 4; i += 32) reinterpret_cast<float4 *>(&s.acc[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1172,26 +1178,29 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6_kernel(const float *__restri
     }
     cp_async_wait<0>();
     __syncwarp();
+    if (G > 1) __syncthreads();
     const bool relu = (flags & GPC_CONV_RELU) != 0;
-    for (int r = 0; r < rows; ++r) {
-        float v = s.acc[r][lane];
+    for (int r = wid; r < rows; r += G) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < G; ++w) v += reinterpret_cast<Sc6Smem<TW, D> *>(smem_raw)[w].acc[r][lane];      // warp order: offsets ascending
         if (residual) v += __ldg(residual + (r0 + r) * GPC_C + lane);
         if (relu) v = fmaxf(v, 0.f);
         y[(r0 + r) * GPC_C + lane] = v;
     }
 }
 
-template <int TW, int D>
+template <int TW, int D, int G = 1>
 static int launch_spconv_v6(const float *x, const void *Wa, const u32 *seg, const u64 *pairs, i64 n, const float *residual,
                             int flags, float *y, cudaStream_t st) {
     static bool configured = false;
-    const size_t smem = sizeof(Sc6Smem<TW, D>);
+    const size_t smem = sizeof(Sc6Smem<TW, D>) * G;
     if (!configured) {
-        GPC_CUDA_CHECK(cudaFuncSetAttribute(spconv_fwd_v6_kernel<TW, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GPC_CUDA_CHECK(cudaFuncSetAttribute(spconv_fwd_v6_kernel<TW, D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const i64 tiles = (n + TW - 1) / TW;
-    spconv_fwd_v6_kernel<TW, D><<<(unsigned)tiles, 32, smem, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y);
+    spconv_fwd_v6_kernel<TW, D, G><<<(unsigned)tiles, 32 * G, smem, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
@@ -1218,6 +1227,19 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
         if (tile_rows == 128) return launch_spconv_v6<128, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 43) {
         if (tile_rows == 64) return launch_spconv_v6<64, 3>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 44) {          // split offsets over 4 warps (coarse levels)
+        if (tile_rows == 8) return launch_spconv_v6<8, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 16) return launch_spconv_v6<16, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 32) return launch_spconv_v6<32, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 46) {          // split offsets over 8 warps
+        if (tile_rows == 8) return launch_spconv_v6<8, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 16) return launch_spconv_v6<16, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 47) {          // split offsets over 16 warps
+        if (tile_rows == 8) return launch_spconv_v6<8, 4, 16>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 45) {          // split offsets over 2 warps
+        if (tile_rows == 16) return launch_spconv_v6<16, 4, 2>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 32) return launch_spconv_v6<32, 4, 2>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 64) return launch_spconv_v6<64, 4, 2>(x, Wa, seg, pairs, n, residual, flags, y, st);
     }
     gpc_set_error("unsupported conv v6 variant %d / tile_rows %d", variant, tile_rows);
     return GPC_EINVAL;

@@ -179,29 +179,24 @@ int gpc_spconv_fwd_v8(const float *x, const void *Wa, const uint32_t *seg, const
                       int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                       void *stream);
 
-/* v9 (variant 70): tcgen05.mma (kind::f16, bf16 hi/lo split, fp32 accumulators in TMEM) over chunks of <= 128 pairs of one
- * offset; CTA tiles of `tile_rows` output rows (pair stream with pad = 1); Wc from gpc_spconv_pack_weights_umma
- * ([125][2][2 KB] canonical K-major no-swizzle images of W[k] hi / lo) */
-int gpc_spconv_pack_weights_umma(const float *W, int n_kernels, void *Wc, void *stream);
-int gpc_spconv_fwd_v9(const float *x, const void *Wc, const uint32_t *seg, const uint64_t *pairs,
-                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
-                      void *stream);
-
-/* "split rows": an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits) -- the
- * operand format of the tcgen05 conv: a gathered row is copied straight into the tensor-core operand tile */
+/* ---- the tcgen05 sparse conv (spconv_tc.cu, spconv_fmt.cu): the kernel the big octree levels run ---- */
+/* "split rows": an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits) -- a gathered
+ * row is a tensor-core operand row as it stands */
 int gpc_rows_split(const float *x, int64_t n, void *xs, void *stream);
 int gpc_rows_join(const void *xs, int64_t n, float *x, void *stream);
-
-/* v10 (variant 80): warp-specialised tcgen05 pipeline (gather warps -> cp.async ring -> tcgen05.mma -> TMEM ->
- * scatter-add warps).  xs = split rows; CTA tiles of cta_rows (256 / 512 / 1024) output rows = 4 quarters, pair stream built
- * with tile_rows = cta_rows / 4 and pad = 1; Wc from gpc_spconv_pack_weights_umma.  Outputs: y (fp32 rows) and / or ys
- * (split rows), either may be NULL.  flags: GPC_CONV_RELU, GPC_CONV_RES_SPLIT (residual points to split rows). */
+/* Wc [n_kernels*125][4 KB]: per offset the canonical K-major (no swizzle) bf16 tiles of W[k]^T, hi then lo */
+int gpc_spconv_pack_weights_umma(const float *W, int n_kernels, void *Wc, void *stream);
+/* y[o,:] = act( sum_k W[k]^T xs[nbr_k(o),:] (+ residual[o,:]) ) with the contraction on the 5th-generation tensor cores:
+ * 17 warps per CTA (8 gather, 1 tcgen05.mma issue, 8 scatter-add); the gathered rows are the MMA's A operand in tensor memory,
+ * W[k] its B operand in shared memory, accumulators D in tensor memory, per-row fp32 sums in shared memory (fixed order).
+ * xs = split rows; CTA tiles of cta_rows (512 / 1024) output rows = 4 quarters; seg / pairs = the pair stream built with
+ * tile_rows = cta_rows / 4 and pad = 1.  Outputs: y (fp32 rows) and / or ys (split rows), either may be NULL.
+ * flags: GPC_CONV_RELU, GPC_CONV_RES_SPLIT (residual points to split rows, else fp32 rows).
+ * profile != 0 runs the instrumented build whose per-role cycle counters gpc_debug_conv_tc_profile returns (host u64[16]). */
 #define GPC_CONV_RES_SPLIT 2
-int gpc_spconv_fwd_v10(const void *xs, const void *Wc, const uint32_t *seg, const uint64_t *pairs, int64_t n,
-                       int cta_rows, const void *residual, int flags, float *y, void *ys, int variant, void *stream);
-
-/* variant 89 = v10 with per-role cycle counters; out_h = host u64[16] (layout: spconv_umma.cu), reset != 0 clears them */
-int gpc_debug_conv_profile(unsigned long long *out_h, int reset);
+int gpc_spconv_fwd_tc(const void *xs, const void *Wc, const uint32_t *seg, const uint64_t *pairs, int64_t n,
+                      int cta_rows, const void *residual, int flags, float *y, void *ys, int profile, void *stream);
+int gpc_debug_conv_tc_profile(unsigned long long *out_h, int reset);
 
 /* ---- a-6/a-9/a-12: embeddings ---- */
 /* out[o,:] = table[idx[o],:]  (prior_embedding, network_ue_4stage_conv.py:15) */

@@ -208,12 +208,11 @@ def test_sparse_conv(env, n, ext):
 
 @pytest.fixture(scope="module")
 def env_umma(env):
-    """A second codec whose levels ALL run the tcgen05 conv (variant 90, split rows), whatever their size."""
+    """A second codec whose levels ALL run the tcgen05 conv (split rows), whatever their size and density."""
     from gauspcc_b200.codec import GausPcgcCodec
     codec = GausPcgcCodec(env["codec"].w, env["dev"])
-    codec.conv_variant = 90
-    codec.umma_min_rows = 1
-    codec.tile_rows = 1024
+    codec.conv_variant = 100
+    codec.tc_min_rows, codec.tc_min_density = 1, 0.0
     return dict(env, codec=codec)
 
 
@@ -224,7 +223,7 @@ def test_sparse_conv_tcgen05(env_umma, n, ext, cta_rows):
     from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
     from oracle import oracle as O
     codec, w = env_umma["codec"], env_umma["w"]
-    codec.adaptive_tiles, codec.tile_rows = False, cta_rows
+    codec.tc_cta_rows = cta_rows
     try:
         xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
         xyz = xyz[O.sort_zyx_perm(xyz)]
@@ -253,7 +252,7 @@ def test_sparse_conv_tcgen05(env_umma, n, ext, cta_rows):
         # deterministic: bit-identical on a second launch (encoder / decoder CDF identity depends on it)
         assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)
     finally:
-        codec.adaptive_tiles, codec.tile_rows = True, 1024
+        codec.tc_cta_rows = 1024
 
 
 @pytest.mark.parametrize("n,seed,ext", [(20000, 1, 16), (2500, 5, 12)])

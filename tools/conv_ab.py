@@ -18,12 +18,14 @@ def main():
     mm = meta.cpu().numpy()[2:8]
     leaf = base.sort_unique(keys, mm.astype(np.uint32))
     levels = base.build_pyramid(leaf, mm.astype(np.int64))
-    sel = [l for l in levels if l.n >= 2000]
+    sel = [l for l in levels if l.n >= int(os.environ.get("AB_MIN_ROWS", 2000)) and l.n <= int(os.environ.get("AB_MAX_ROWS", 1 << 30))]
     ref = {}
     print("levels:", [l.n for l in levels])
     for variant, tr in configs:
         codec = GausPcgcCodec(w, dev, tile_rows=tr)
         codec.conv_variant = variant
+        if variant >= 100:
+            codec.tc_cta_rows, codec.tc_min_density = tr, 0.0
         tot_ms, tot_pairs = 0.0, 0
         line = []
         for li, lv in enumerate(sel):
@@ -40,8 +42,8 @@ def main():
             err = float((y - ref[li]).abs().max())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
-            if variant in (89, 99):
-                codec.lib.gpc_debug_conv_profile(None, 1)
+            if variant == 101:
+                codec.lib.gpc_debug_conv_tc_profile(None, 1)
             e0.record()
             for _ in range(reps):
                 codec.conv(xin, 3, km, relu=True, out=y)
@@ -49,16 +51,15 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             tot_ms += ms; tot_pairs += km.n_real
             clk = ms * 1e-3 * 1.9e9 * 148 / max(km.n_real, 1)
-            if variant in (89, 99) and km.cta_rows:
+            if variant == 101 and km.cta_rows:
                 import ctypes
                 buf = (ctypes.c_uint64 * 32)()
-                codec.lib.gpc_debug_conv_profile(ctypes.cast(buf, ctypes.c_void_p), 1)
+                codec.lib.gpc_debug_conv_tc_profile(ctypes.cast(buf, ctypes.c_void_p), 1)
                 ch = max(buf[9], 1)
                 names = ["g.empty", "g.issue", "g.wait", "m.full", "m.dempty", "m.issue", "e.dfull", "e.ld", "e.rmw"]
                 ctas = reps * ((lv.n + km.cta_rows - 1) // km.cta_rows)
                 print(f"   prof n={lv.n}: chunks/cta={ch / ctas:.0f} " + " ".join(f"{nm}={buf[i] / ch:.0f}" for i, nm in enumerate(names))
-                      + f" | per cta: total={buf[10] / ctas:.0f} setup={buf[11] / ctas:.0f} writeout={buf[12] / ctas:.0f}"
-                      + " | fine " + " ".join(f"{buf[16 + i] / ch:.0f}" for i in range(10)))
+                      + f" | per cta: total={buf[10] / ctas:.0f} setup={buf[11] / ctas:.0f} writeout={buf[12] / ctas:.0f}")
             line.append(f"n={lv.n} tiles={km.n_tiles} p/r={km.n_real / lv.n:.1f} {ms:.3f}ms {clk:.1f}clk/pair err={err:.1e}")
         print(f"variant {variant} tile {tr}: total {tot_ms:.2f} ms, {tot_ms * 1e-3 * 1.9e9 * 148 / tot_pairs:.1f} clk/pair/SM")
         for l in line:
