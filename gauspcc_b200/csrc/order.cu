@@ -123,11 +123,19 @@ extern "C" int gpc_make_xform_h(const uint32_t *mm, gpc_key_xform *xf) {
     return GPC_OK;
 }
 
-// ---------------------------------------------------------------- radix sort
-constexpr int RS_THREADS = 256;
+// ---------------------------------------------------------------- radix sort ("onesweep": one read + one write of the records per pass)
+// LSD, 8-bit digits over the compacted key.  ONE up-front kernel reads the keys once and builds the global digit histogram of every
+// pass; each pass is then a single kernel: a tile ranks its 4096 records (warp match_any, no atomics on the order), publishes its
+// per-digit counts, and finds where its digits start in the output by DECOUPLED LOOK-BACK over the tiles before it (Merrill &
+// Garland's single-pass scan, as used by Adinets & Merrill's onesweep sort) instead of a separate per-tile histogram kernel plus a
+// device-wide scan per pass.  Traffic per record: 8 B once, then 12 B in + 12 B out per pass (the 3-kernel version read the keys twice
+// per pass).  Tiles take their index from an atomic counter, so a tile only ever waits for tiles that are already running.
+constexpr int RS_THREADS = 512;       // 2 CTAs of 16 warps per SM (64 registers per thread): the pass is latency-bound, occupancy is what it needs
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 16;
+constexpr int RS_IPT = 8;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;
+constexpr int RS_MAX_PASSES = 8;
+constexpr u32 RS_FLAG_AGG = 1u << 30, RS_FLAG_INCL = 2u << 30, RS_FLAG_MASK = 3u << 30, RS_VAL_MASK = ~RS_FLAG_MASK;
 
 template <bool XF>
 __device__ __forceinline__ u32 rs_digit(u64 key, const gpc_key_xform &xf, int shift) {
@@ -135,44 +143,74 @@ __device__ __forceinline__ u32 rs_digit(u64 key, const gpc_key_xform &xf, int sh
     return (u32)(c >> shift) & 0xFFu;
 }
 
+// ghist[p][d] = number of keys whose p-th digit is d (all passes from one read of the keys)
 template <bool XF>
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const u64 *__restrict__ keys, i64 n, gpc_key_xform xf,
-                                                             int shift, u32 *__restrict__ hist, int nblocks) {
-    __shared__ u32 h[256];
-    h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(256) rs_global_hist_kernel(const u64 *__restrict__ keys, i64 n, gpc_key_xform xf, int passes,
+                                                             u32 *__restrict__ ghist) {
+    __shared__ u32 h[RS_MAX_PASSES][256];
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += 256) (&h[0][0])[i] = 0;
     __syncthreads();
-    const i64 base = (i64)blockIdx.x * RS_TILE;
-#pragma unroll
-    for (int r = 0; r < RS_IPT; ++r) {
-        i64 idx = base + r * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&h[rs_digit<XF>(keys[idx], xf, shift)], 1u);
+    const int lane = threadIdx.x & 31;
+    for (i64 i0 = (i64)blockIdx.x * 256 + (threadIdx.x & ~31); i0 < n; i0 += (i64)gridDim.x * 256) {      // warp-uniform trip count
+        const i64 i = i0 + lane;
+        const bool valid = i < n;
+        const u64 c = valid ? (XF ? key_compact(keys[i], xf) : keys[i]) : 0ull;
+        const u32 nvalid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+        for (int p = 0; p < passes; ++p) {
+            const u32 d = (u32)(c >> (8 * p)) & 0xFFu;
+            const u32 d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
+            // sorted or clustered inputs: the high digits of a warp's 32 keys are usually all equal -> one add instead of a 32-way conflict
+            if (__all_sync(0xFFFFFFFFu, !valid || d == d0)) { if (lane == 0) atomicAdd(&h[p][d0], nvalid); }
+            else if (valid) atomicAdd(&h[p][d], 1u);
+        }
     }
     __syncthreads();
-    hist[(i64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+    for (int i = threadIdx.x; i < passes * 256; i += 256) {
+        const u32 v = (&h[0][0])[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+// in place: ghist[p][d] -> number of keys whose p-th digit is < d
+__global__ void __launch_bounds__(256) rs_scan_hist_kernel(u32 *__restrict__ ghist) {
+    __shared__ u32 wsum[8];
+    u32 *g = ghist + blockIdx.x * 256;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 v = g[tid];
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 off = 0;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    g[tid] = off + incl - v;
 }
 
-// Stable scatter of one tile.  Ranks come from warp-level match_any (no atomics on the output order); the tile is first
-// re-ordered by digit in shared memory, so that the global writes are contiguous runs per digit (a 4096-key tile over
-// 256 digits = 128-byte runs) instead of one 8 + 4 byte record per thread at a random address.
+// Stable scatter of one tile.  The tile is first re-ordered by digit in shared memory, so that the global writes are contiguous runs
+// per digit (a 4096-key tile over 256 digits = 128-byte runs) instead of one 8 + 4 byte record per thread at a random address.
 struct RsSmem {
     u64 keys[RS_TILE];
     u32 vals[RS_TILE];
     u32 whist[RS_WARPS][256];
     u32 dstart[256];
     u32 gbase[256];
+    u32 tile;
 };
 
 template <bool XF, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
-                                                                u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, i64 n,
-                                                                gpc_key_xform xf, int shift,
-                                                                const u32 *__restrict__ hist_scanned, int nblocks) {
+__global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+                                                                 u64 *__restrict__ keys_out, u32 *__restrict__ vals_out, i64 n,
+                                                                 gpc_key_xform xf, int shift, const u32 *__restrict__ ghist_scanned,
+                                                                 u32 *__restrict__ status /* [tiles][256], zeroed */,
+                                                                 u32 *__restrict__ tile_counter) {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RsSmem &s = *reinterpret_cast<RsSmem *>(rs_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s.tile = atomicAdd(tile_counter, 1u);          // tiles start in index order: look-back never waits on a tile that has not started
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s.whist[0][0])[i] = 0;
     __syncthreads();
-    const i64 tbase = (i64)blockIdx.x * RS_TILE;
+    const u32 tile = s.tile;
+    const i64 tbase = (i64)tile * RS_TILE;
     const i64 wbase = tbase + (i64)warp * (32 * RS_IPT);
     u64 k[RS_IPT];
     u32 v[RS_IPT], rk[RS_IPT];
@@ -197,23 +235,41 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
         rk[r] = prev + lower;
     }
     __syncthreads();
-    {   // per digit: exclusive scan across warps, then exclusive scan across digits (tile-local start of each digit)
-        const int d = tid;
-        u32 off = 0;
+    // thread d < 256: count of digit d in this tile (exclusive scan across warps), publish it, look back, tile-local start of each digit
+    const int d = tid;
+    u32 off = 0, before = 0, incl = 0;
+    if (tid < 256) {
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { u32 t = s.whist[w][d]; s.whist[w][d] = off; off += t; }
-        // off = number of keys of digit d in this tile; block-wide exclusive scan over the 256 digits
-        u32 incl = off;
+        volatile u32 *st = status + (size_t)tile * 256 + d;
+        if (tile > 0) *st = RS_FLAG_AGG | off;
+        for (i64 t = (i64)tile - 1; t >= 0; --t) {   // records of digit d in the tiles before this one
+            volatile const u32 *ps = status + (size_t)t * 256 + d;
+            u32 w = *ps, spins = 0;
+            while ((w & RS_FLAG_MASK) == 0) {        // bounded: a broken protocol must fault the launch, never hang the GPU
+                if (++spins > (1u << 26)) __trap();
+                w = *ps;
+            }
+            before += w & RS_VAL_MASK;
+            if ((w & RS_FLAG_MASK) == RS_FLAG_INCL) break;
+        }
+        *st = RS_FLAG_INCL | (before + off);
+        incl = off;                                  // block-wide exclusive scan over the 256 digit counts
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-        s.gbase[d] = incl;                       // temporarily: inclusive within the warp's 32 digits
-        __syncthreads();
+        s.gbase[d] = incl;                           // temporarily: inclusive within the warp's 32 digits
+    }
+    __syncthreads();
+    u32 start = 0;
+    if (tid < 256) {
         u32 warp_off = 0;
         for (int w = 0; w < warp; ++w) warp_off += s.gbase[w * 32 + 31];
-        const u32 start = warp_off + incl - off;
-        __syncthreads();
+        start = warp_off + incl - off;
+    }
+    __syncthreads();
+    if (tid < 256) {
         s.dstart[d] = start;
-        s.gbase[d] = hist_scanned[(i64)d * nblocks + blockIdx.x] - start;
+        s.gbase[d] = ghist_scanned[d] + before - start;
     }
     __syncthreads();
 #pragma unroll
@@ -236,21 +292,23 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const u64 *__res
 }
 
 struct SortWs {
-    u32 *hist, *hist_scanned;
-    void *scan_ws;
+    u32 *ghist;          // [RS_MAX_PASSES][256]
+    u32 *counters;       // [RS_MAX_PASSES]
+    u32 *status;         // [passes][tiles][256]
     u64 *alt_keys;
     u32 *alt_vals;
+    size_t zero_bytes;   // ghist + counters + status are contiguous and zeroed by one memset
     size_t total;
 };
 static SortWs sort_ws_layout(void *ws, i64 n) {
     SortWs L;
     const i64 nblocks = (n + RS_TILE - 1) / RS_TILE;
-    const i64 nh = 256 * (nblocks > 0 ? nblocks : 1);
     size_t off = 0;
     char *b = (char *)ws;
-    L.hist = (u32 *)(b + off); off += align_up((size_t)nh * 4, 256);
-    L.hist_scanned = (u32 *)(b + off); off += align_up((size_t)(nh + 1) * 4, 256);
-    L.scan_ws = b + off; off += align_up(scan_workspace_bytes<u32>(nh), 256);
+    L.ghist = (u32 *)(b + off); off += RS_MAX_PASSES * 256 * 4;
+    L.counters = (u32 *)(b + off); off += 256;
+    L.status = (u32 *)(b + off); off += align_up((size_t)RS_MAX_PASSES * (size_t)(nblocks > 0 ? nblocks : 1) * 256 * 4, 256);
+    L.zero_bytes = off;
     L.alt_keys = (u64 *)(b + off); off += align_up((size_t)(n > 0 ? n : 1) * 8, 256);
     L.alt_vals = (u32 *)(b + off); off += align_up((size_t)(n > 0 ? n : 1) * 4, 256);
     L.total = off;
@@ -263,18 +321,25 @@ static int sort_pairs_impl(const u64 *keys_in, const u32 *vals_in, u64 *keys_out
                            gpc_key_xform xf, int total_bits, void *ws, size_t ws_bytes, cudaStream_t st) {
     GPC_REQUIRE(vals_out != nullptr && keys_out != nullptr, GPC_EINVAL, "keys_out and vals_out are required");
     GPC_REQUIRE(keys_out != keys_in, GPC_EINVAL, "sort is out of place");
+    GPC_REQUIRE(n < (1ll << 30), GPC_EINVAL, "n must be < 2^30");
     if (n <= 0) return GPC_OK;
     SortWs L = sort_ws_layout(ws, n);
     GPC_REQUIRE(ws && ws_bytes >= L.total, GPC_ENOSPC, "sort workspace too small");
     static bool configured = false;
     if (!configured) {
-        GPC_CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<XF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        GPC_CUDA_CHECK(cudaFuncSetAttribute(rs_scatter_kernel<XF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        GPC_CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<XF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        GPC_CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<XF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         configured = true;
     }
     const int P = (total_bits + 7) / 8;
+    GPC_REQUIRE(P <= RS_MAX_PASSES, GPC_EINVAL, "key wider than 64 bits");
     const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
     const int passes = P == 0 ? 1 : P;     // all keys equal: one pass over a zero digit = stable identity
+    GPC_CUDA_CHECK(cudaMemsetAsync(L.ghist, 0, (size_t)((char *)L.status - (char *)L.ghist) + (size_t)passes * nblocks * 256 * 4, st));
+    rs_global_hist_kernel<XF><<<min(cdiv(n, 256 * 16), 148u * 8u), 256, 0, st>>>(keys_in, n, xf, passes, L.ghist);
+    GPC_LAUNCH_CHECK();
+    rs_scan_hist_kernel<<<passes, 256, 0, st>>>(L.ghist);
+    GPC_LAUNCH_CHECK();
     const u64 *src_k = keys_in;
     const u32 *src_v = vals_in;
     for (int p = 0; p < passes; ++p) {
@@ -283,15 +348,13 @@ static int sort_pairs_impl(const u64 *keys_in, const u32 *vals_in, u64 *keys_out
         u64 *dst_k = to_out ? keys_out : L.alt_keys;
         u32 *dst_v = to_out ? vals_out : L.alt_vals;
         const int shift = 8 * p;
-        rs_hist_kernel<XF><<<nblocks, RS_THREADS, 0, st>>>(src_k, n, xf, shift, L.hist, nblocks);
-        GPC_LAUNCH_CHECK();
-        PtrLoad<u32> pl{L.hist};
-        int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, (i64)256 * nblocks, L.hist_scanned, L.scan_ws, st);
-        if (rc) return rc;
+        u32 *status = L.status + (size_t)p * nblocks * 256;
         if (p == 0 && src_v == nullptr)
-            rs_scatter_kernel<XF, true><<<nblocks, RS_THREADS, sizeof(RsSmem), st>>>(src_k, nullptr, dst_k, dst_v, n, xf, shift, L.hist_scanned, nblocks);
+            rs_onesweep_kernel<XF, true><<<nblocks, RS_THREADS, sizeof(RsSmem), st>>>(src_k, nullptr, dst_k, dst_v, n, xf, shift, L.ghist + p * 256,
+                                                                                     status, L.counters + p);
         else
-            rs_scatter_kernel<XF, false><<<nblocks, RS_THREADS, sizeof(RsSmem), st>>>(src_k, src_v, dst_k, dst_v, n, xf, shift, L.hist_scanned, nblocks);
+            rs_onesweep_kernel<XF, false><<<nblocks, RS_THREADS, sizeof(RsSmem), st>>>(src_k, src_v, dst_k, dst_v, n, xf, shift, L.ghist + p * 256,
+                                                                                      status, L.counters + p);
         GPC_LAUNCH_CHECK();
         src_k = dst_k; src_v = dst_v;
     }

@@ -1155,14 +1155,19 @@ __global__ void __launch_bounds__(32 * G) spconv_fwd_v6_kernel(const float *__re
         split_bf16(xa.z, xa.w, y1[0][1], y2[0][1]);
         split_bf16(xc.x, xc.y, y1[1][0], y2[1][0]);
         split_bf16(xc.z, xc.w, y1[1][1], y2[1][1]);
-        // F. scatter-add tile c: d[mt][0] = (co 16mt+g, pair 2t), [1] = (co, pair 2t+1), [2]/[3] = co+8
-        if (row_a != 0xFFFFu) {
-            float *a = &s.acc[row_a][g];
-            a[0] += d[0][0]; a[8] += d[0][2]; a[16] += d[1][0]; a[24] += d[1][2];
-        }
-        if (row_b != 0xFFFFu) {
-            float *a = &s.acc[row_b][g];
-            a[0] += d[0][1]; a[8] += d[0][3]; a[16] += d[1][1]; a[24] += d[1][3];
+        // F. scatter-add tile c: d[mt][0] = (co 16mt+g, pair 2t), [1] = (co, pair 2t+1), [2]/[3] = co+8.  The two pairs of a lane
+        // belong to ONE offset, hence to different rows: all eight loads are issued before the first store (written as two
+        // separate read-modify-writes the compiler has to assume they alias and serialises load - add - store - load - add - store)
+        {
+            const bool va = row_a != 0xFFFFu, vb = row_b != 0xFFFFu;
+            float *pa = &s.acc[va ? row_a : 0u][g], *pb = &s.acc[vb ? row_b : 0u][g];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            if (va) { a0 = pa[0]; a1 = pa[8]; a2 = pa[16]; a3 = pa[24]; }
+            if (vb) { b0 = pb[0]; b1 = pb[8]; b2 = pb[16]; b3 = pb[24]; }
+            a0 += d[0][0]; a1 += d[0][2]; a2 += d[1][0]; a3 += d[1][2];
+            b0 += d[0][1]; b1 += d[0][3]; b2 += d[1][1]; b3 += d[1][3];
+            if (va) { pa[0] = a0; pa[8] = a1; pa[16] = a2; pa[24] = a3; }
+            if (vb) { pb[0] = b0; pb[8] = b1; pb[16] = b2; pb[24] = b3; }
         }
         // G. rotate
 #pragma unroll
