@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpcgc.so")
+LIB_PATH = os.environ.get("GPC_LIB_PATH", os.path.join(_HERE, "libgpcgc.so"))      # override: A/B builds of the same ABI (tools/)
 
 c_vp, c_i64, c_int, c_sz, c_f32 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_float
 

@@ -48,6 +48,9 @@ __device__ __forceinline__ void tmem_ld16(u32 taddr, u32 (&d)[16]) {
 }
 
 // ---- mbarrier
+#ifndef TC_POLL_SLEEP_NS
+#define TC_POLL_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -63,6 +66,7 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
+        if (TC_POLL_SLEEP_NS) __nanosleep(TC_POLL_SLEEP_NS);
     }
     __trap();
 }
