@@ -528,8 +528,10 @@ class GausPcgcCodec:
 
     # ------------------------------------------------------------------ decode
     def decode(self, base_xyz: np.ndarray, base_occ: np.ndarray, streams: List[bytes], scale: float = 1.0,
-               forced_occ: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
-        """-> float32 [N,3] CUDA, rows in the reference's order (children of (z,y,x)-sorted parents, octant ascending).
+               forced_occ: Optional[List[torch.Tensor]] = None, sorted_rows: bool = False) -> torch.Tensor:
+        """-> float32 [N,3] CUDA, rows in the reference's order (children of (z,y,x)-sorted parents, octant ascending), or,
+        with sorted_rows, in ascending (z,y,x) == calculate_morton_order order (the caller's re-sort,
+        HAC/scene/gaussian_model.py:1253-1255, becomes the identity).
 
         forced_occ (bench only): per-level ground-truth occupancy already on the device; the GPU work is
         then identical to a real decode but the host range decoder is skipped ("device-timed" number).
@@ -539,8 +541,8 @@ class GausPcgcCodec:
         if len(streams) % 4:
             raise ValueError("stream count must be a multiple of 4 (one group per octree level)")
         self._seg_begin()
-        bx = torch.from_numpy(np.ascontiguousarray(base_xyz, dtype=np.int32).reshape(-1, 3)).to(self.dev)
-        bo = torch.from_numpy(np.ascontiguousarray(base_occ, dtype=np.uint8).reshape(-1)).to(self.dev)
+        bx = torch.from_numpy(np.array(base_xyz, dtype=np.int32).reshape(-1, 3)).to(self.dev)
+        bo = torch.from_numpy(np.array(base_occ, dtype=np.uint8).reshape(-1)).to(self.dev)
         keys, meta = self.pack_keys(bx)
         meta_h = meta.cpu().numpy()
         if meta_h[0] & 2:
@@ -588,10 +590,14 @@ class GausPcgcCodec:
             cur = child
         n_pts = int(np.unpackbits(cur.occ.cpu().numpy()).sum())
         out = self._empty((n_pts, 3), torch.float32)
-        ws_b = self.lib.gpc_expand_workspace_bytes(cur.n)
-        ws = self._ws(ws_b)
-        self._call("gpc_expand_leaves_f32", _ptr(cur.keys), _ptr(cur.occ), cur.n, n_pts, float(scale), _ptr(out), _ptr(ws), ws_b,
-                   self._stream())
+        if sorted_rows:
+            ck, _ = self.expand(cur, n_pts)            # child keys already in (z,y,x) order: closed-form ranks, no sort
+            self._call("gpc_unpack_keys_f32", _ptr(ck), n_pts, float(scale), _ptr(out), self._stream())
+        else:
+            ws_b = self.lib.gpc_expand_workspace_bytes(cur.n)
+            ws = self._ws(ws_b)
+            self._call("gpc_expand_leaves_f32", _ptr(cur.keys), _ptr(cur.occ), cur.n, n_pts, float(scale), _ptr(out), _ptr(ws), ws_b,
+                       self._stream())
         self._seg_end()
         self.last_stats = {"gpu_ms": self._seg_total_ms(), "launches": self.launches, "host_ac_s": t_ac, "gpu_wait_s": t_wait}
         return out

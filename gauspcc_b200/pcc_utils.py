@@ -132,13 +132,17 @@ def decompress_point_cloud(
     output_path=None,        # Path for output ply file (optional)
     channels=32,             # Network channel count
     kernel_size=5,           # Convolution kernel size
-    is_data_pre_quantized=True  # Whether original point cloud is pre-quantized
+    is_data_pre_quantized=True,  # Whether original point cloud is pre-quantized
+    sorted_output=False      # extension (not in the reference): rows in calculate_morton_order order
 ):
     """
     Decompress point cloud from bin file (reference: pcc_utils.py:230-400).
 
     Returns {'dec_time', 'num_points', 'point_cloud': float32 [N,3] on the GPU, 'output_path'}.  Row
     order is the reference's: children of the (z,y,x)-sorted last level, octant ascending (:375).
+    With sorted_output=True the rows come back in ascending (z,y,x) instead, which is the order
+    calculate_morton_order produces: the re-sort HAC does right after this call
+    (HAC/scene/gaussian_model.py:1253-1255) is then the identity permutation and can be dropped.
     """
     if output_path:
         os.makedirs(os.path.dirname(output_path), exist_ok=True)
@@ -150,7 +154,7 @@ def decompress_point_cloud(
 
     torch.cuda.synchronize(dev)
     dec_time_start = time.time()
-    scan = codec.decode(base_xyz, base_occ, streams, scale=float(posQ))
+    scan = codec.decode(base_xyz, base_occ, streams, scale=float(posQ), sorted_rows=bool(sorted_output))
     if not is_data_pre_quantized:
         scan = (scan - 131072) * 0.001                 # pcc_utils.py:381
     torch.cuda.synchronize(dev)

@@ -407,6 +407,48 @@ def test_pcc_utils_api(env, tmp_path):
         pcc_utils.compress_point_cloud(xyz[:100], bad, str(tmp_path / "b4" / "x.bin"))
 
 
+def test_sorted_output_is_morton_order(env, tmp_path):
+    """decompress_point_cloud(sorted_output=True) hands the rows back in calculate_morton_order order, so the re-sort
+    at HAC/scene/gaussian_model.py:1253-1255 is the identity."""
+    from gauspcc_b200 import pcc_utils
+    from gauspcc_b200.synth import hac_like_cloud
+    from gauspcc_b200.weights import save_synthetic_checkpoint
+    ckpt = save_synthetic_checkpoint(str(tmp_path / "GausPcgc" / "best_model_ue_4stage_conv.pt"))
+    xyz = hac_like_cloud(30000, 3)
+    x = torch.tensor(xyz, dtype=torch.float32, device=env["dev"])
+    binp = str(tmp_path / "out" / "xyz_pcc.bin")
+    pcc_utils.compress_point_cloud(x, ckpt, binp)
+    ref_order = pcc_utils.decompress_point_cloud(binp, ckpt)["point_cloud"]
+    srt = pcc_utils.decompress_point_cloud(binp, ckpt, sorted_output=True)["point_cloud"]
+    perm = pcc_utils.calculate_morton_order(srt)
+    assert torch.equal(perm, torch.arange(srt.shape[0], device=perm.device))
+    assert torch.equal(srt, ref_order[pcc_utils.calculate_morton_order(ref_order)])
+    assert np.array_equal(np.unique(srt.cpu().numpy().astype(np.int32), axis=0), np.unique(xyz, axis=0))
+
+
+def test_cli_file_roundtrip(env, tmp_path):
+    """the stand-alone compress / decompress tools over files, metric coordinates and posQ (lossless on the voxel set)."""
+    from gauspcc_b200 import cli
+    from gauspcc_b200.weights import save_synthetic_checkpoint
+    ckpt = save_synthetic_checkpoint(str(tmp_path / "GausPcgc" / "best_model_ue_4stage_conv.pt"))
+    rng = np.random.default_rng(4)
+    src = tmp_path / "in"
+    src.mkdir()
+    pts = (rng.normal(size=(20000, 3)) * np.array([8.0, 8.0, 1.0])).astype(np.float32)         # metres, KITTI-like
+    np.concatenate([pts, np.ones((20000, 1), np.float32)], axis=1).tofile(src / "000001.bin")
+    np.save(src / "000002.npy", pts[:5000].astype(np.float64) * 0.5)
+    rows = cli.compress_files(str(src), str(tmp_path / "cmp"), ckpt, posQ=16, resultdir=str(tmp_path / "res"))
+    assert [r["filedir"] for r in rows] == ["000001.bin", "000002.npy"] and all(r["bpp"] > 0 for r in rows)
+    assert os.path.exists(tmp_path / "res" / "ue_4stage_conv_data2.csv")
+    drows = cli.decompress_files(str(tmp_path / "cmp"), str(tmp_path / "dec"), ckpt)
+    assert [r["filedir"] for r in drows] == ["000001.bin.bin", "000002.npy.bin"]
+    for name, p in (("000001.bin", pts.astype(np.float64)), ("000002.npy", pts[:5000].astype(np.float64) * 0.5)):
+        q = np.unique(cli.quantise(p, 16, False).numpy(), axis=0)
+        dec = cli.read_points(str(tmp_path / "dec" / (name + ".bin.ply")))
+        back = np.unique(np.round((dec / 0.001 + 131072) / 16).astype(np.int32), axis=0)          # undo decompress_ue_4stage_conv.py:176-179
+        assert drows[0]["num_points"] > 0 and np.array_equal(back, q)
+
+
 def test_full_size_roundtrip_1m(env):
     """BASELINE config 2 size: lossless round trip, encoder == decoder CDFs (else the range decoder
     desynchronises and the geometry is garbage), teacher-forced decode == real decode."""
