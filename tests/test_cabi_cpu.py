@@ -79,6 +79,28 @@ def test_host_range_coder_matches_oracle(A, n):
     assert np.array_equal(O.ac_decode(cdf, got).astype(np.uint8), sym)
 
 
+@pytest.mark.parametrize("A", [2, 4, 16])
+def test_host_range_decoder_underflow_heavy(A):
+    """Long streams whose intervals keep straddling the midpoint (boundaries one step off 1/2) and keep carrying: the decoder's
+    one-step underflow renormalisation (4- and 16-ary) and its loop form (binary) against the oracle's bit-at-a-time decoder."""
+    lib = _lib.load()
+    rng = np.random.default_rng(77 + A)
+    n = 60000
+    cdf = np.zeros((n, A + 1), dtype=np.uint16)
+    half = A // 2
+    for i in range(n):
+        mid = 32768 + int(rng.integers(-2, 3))                     # the boundary between the two halves of the alphabet
+        lo = np.sort(rng.choice(np.arange(1, mid), size=half - 1, replace=False)) if half > 1 else np.zeros(0, int)
+        hi = np.sort(rng.choice(np.arange(mid + 1, 65535), size=A - half - 1, replace=False)) if A - half > 1 else np.zeros(0, int)
+        cdf[i, 1:A] = np.concatenate([lo, [mid], hi])
+    sym = rng.integers(half - 1, half + 1, size=n).astype(np.uint8)      # always next to the midpoint
+    sym[::97] = rng.integers(0, A, size=len(sym[::97]))
+    stream = _enc(lib, cdf, sym)
+    assert stream == O.ac_encode(cdf, sym.astype(np.int16))
+    assert np.array_equal(_dec(lib, cdf, stream), sym)
+    assert np.array_equal(O.ac_decode(cdf, stream).astype(np.uint8), sym)
+
+
 def test_host_range_coder_rejects_bad_symbol():
     lib = _lib.load()
     cdf = np.array([[0, 100, 0]], dtype=np.uint16)
