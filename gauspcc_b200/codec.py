@@ -162,6 +162,19 @@ class GausPcgcCodec:
         self._ev_next += 2
         return e0, e1
 
+    def prewarm_profile_events(self, n_events: int):
+        """bench.py: torch creates a CUDA event lazily at its first record(); do that for every event the timed region will use
+        BEFORE the timed region (each creation is tens of microseconds of host time between two launches)."""
+        if not hasattr(self, "_ev_pool"):
+            self._ev_pool, self._ev_next = [], 0
+        while len(self._ev_pool) < n_events:
+            self._ev_pool.append(torch.cuda.Event(enable_timing=True))
+        st = torch.cuda.current_stream(self.dev)
+        for e in self._ev_pool[:n_events]:
+            e.record(st)
+        torch.cuda.synchronize(self.dev)
+        self._ev_next = 0
+
     def _call(self, name, *args):
         _lib.check(getattr(self.lib, name)(*args), name)
 
