@@ -64,6 +64,11 @@ SIGNATURES = {
     "gpc_spconv_fwd_v7": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_spconv_fwd_v8": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_spconv_pack_weights_umma": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "gpc_kmap_sparse_segments": (c_i64, [c_i64]),
+    "gpc_kmap_sparse_workspace_bytes": (c_sz, [c_i64]),
+    "gpc_kmap_sparse_count": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_kmap_sparse_fill": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gpc_spconv_sparse_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_vp]),
     "gpc_rows_split": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "gpc_rows_join": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "gpc_spconv_fwd_tc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),

@@ -52,6 +52,9 @@ class KMap:
     cta_rows: int = 0                         # > 0: tcgen05 conv; tile_rows == cta_rows / 4 (the quarters of a CTA tile)
     _fill: object = None
     v6_variant: int = 42                      # mma.sync conv: 42 = one warp per tile, 45 / 46 / 47 = offsets split over 2 / 8 / 16 warps
+    sparse: bool = False                      # sparse big level: centre product + offset-sorted stragglers (spconv_sparse.cu)
+    rowptr: Optional[torch.Tensor] = None     # sparse: first contribution of every row
+    contrib: Optional[torch.Tensor] = None    # sparse: scratch [stragglers, 32] fp32, rewritten by every conv on the level
 
 
 @dataclass
@@ -111,6 +114,12 @@ class GausPcgcCodec:
         self.tc_min_rows = int(os.environ.get("GPC_TC_MIN_ROWS", 150_000))
         self.tc_min_density = float(os.environ.get("GPC_TC_MIN_DENSITY", 5.0))
         self.tc_cta_rows = int(os.environ.get("GPC_TC_CTA_ROWS", 1024))
+        # big levels with fewer pairs per row than this run the centre + stragglers conv (spconv_sparse.cu); 0 disables it.
+        # Density only falls from one octree level to the next finer one, so after the first sparse level the finer ones skip
+        # the tiled count (both encoder and decoder walk the levels coarse -> fine and take the same decisions).
+        self.sparse_max_density = float(os.environ.get("GPC_SPARSE_MAX_DENSITY", 4.5))
+        self.sparse_min_rows = int(os.environ.get("GPC_SPARSE_MIN_ROWS", 150_000))
+        self._seen_sparse = False
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -288,6 +297,23 @@ class GausPcgcCodec:
                                       n_pairs if pad > 1 else 0, self._stream())
         return km
 
+    def _sparse_map(self, dense: torch.Tensor, n: int) -> KMap:
+        m = int(self.lib.gpc_kmap_sparse_segments(n))
+        seg = self._empty((m + 1,), torch.int32)
+        rowptr = self._empty((n + 1,), torch.int32)
+        tot = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        ws_b = self.lib.gpc_kmap_sparse_workspace_bytes(n)
+        ws = self._ws(ws_b)
+        self._call("gpc_kmap_sparse_count", _ptr(dense), n, _ptr(seg), _ptr(rowptr), _ptr(tot), _ptr(ws), ws_b, self._stream())
+        n_entries, n_strag = (int(v) for v in tot.tolist())
+        pairs = self._empty((max(n_entries, 1),), torch.int64)
+        self._call("gpc_kmap_sparse_fill", _ptr(dense), n, _ptr(seg), _ptr(rowptr), _ptr(ws), _ptr(pairs), n_entries, self._stream())
+        km = KMap(seg, None, None, pairs, n_entries, 0)
+        km.n_real = n + n_strag
+        km.sparse, km.rowptr = True, rowptr
+        km.contrib = self._empty((max(n_strag, 1), 32), torch.float32)
+        return km
+
     def build_kmap(self, keys: torch.Tensor, keep_dense: bool = False):
         n = keys.shape[0]
         cap = self.lib.gpc_hash_capacity(n)
@@ -311,6 +337,9 @@ class GausPcgcCodec:
             self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
             return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
         km = None
+        sparse_ok = self.conv_variant in (42, 100) and self.sparse_max_density > 0 and not keep_dense and n >= self.sparse_min_rows
+        if sparse_ok and self._seen_sparse:
+            return self._sparse_map(dense, n)
         if self.conv_variant >= 100 and not keep_dense and n >= self.tc_min_rows:
             km = self._pair_stream(dense, n, self.tc_cta_rows // 4, 1, False)        # quarters of a tcgen05 CTA tile
             if km.n_real >= self.tc_min_density * n:
@@ -322,6 +351,9 @@ class GausPcgcCodec:
             tr, v6v = self._v6_config(n)
             km = self._pair_stream(dense, n, tr, pad, self.conv_variant < 10 or keep_dense)
             km.v6_variant = v6v
+            if sparse_ok and km.n_real < self.sparse_max_density * n:
+                self._seen_sparse = True
+                return self._sparse_map(dense, n)
         km._fill()
         km._fill = None
         return (km, dense) if keep_dense else km
@@ -356,6 +388,13 @@ class GausPcgcCodec:
         if self.conv_profile is not None:
             e0, e1 = self._profile_events()
             e0.record(torch.cuda.current_stream(self.dev))
+        if km.sparse:
+            self._call("gpc_spconv_sparse_fwd", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), _ptr(km.rowptr), n,
+                       km.n_pairs, _ptr(km.contrib), _ptr(residual), 1 if relu else 0, _ptr(y), self._stream())
+            if self.conv_profile is not None:
+                e1.record(torch.cuda.current_stream(self.dev))
+                self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
+            return y
         wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
         if self.conv_variant >= 100 or self.conv_variant == 42:
             self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
@@ -477,6 +516,7 @@ class GausPcgcCodec:
         """
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
+        self._seen_sparse = False
         self._seg_begin()
         xyz = xyz.contiguous()
         keys, meta = self.pack_keys(xyz)
@@ -551,6 +591,7 @@ class GausPcgcCodec:
         """
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
+        self._seen_sparse = False
         if len(streams) % 4:
             raise ValueError("stream count must be a multiple of 4 (one group per octree level)")
         self._seg_begin()

@@ -179,6 +179,22 @@ int gpc_spconv_fwd_v8(const float *x, const void *Wa, const uint32_t *seg, const
                       int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                       void *stream);
 
+/* ---- the conv of the SPARSE big levels (spconv_sparse.cu): dense centre product + offset-sorted "stragglers" ----
+ * For levels with ~1-4 neighbours per row (the finest octree levels).  Sparse map: seg u32[gpc_kmap_sparse_segments(n) + 1]
+ * (first entry of every (block of 8192 rows, offset != centre) segment, padded to 8 entries), pairs u64[entries] = nbr | dst << 32
+ * (all ones = padding; dst = rowptr[row] + rank of the offset among the row's neighbours), rowptr u32[n + 1].
+ * totals = device u32[2]: {entries, true stragglers}.  ws (gpc_kmap_sparse_workspace_bytes) is shared by count and fill. */
+int64_t gpc_kmap_sparse_segments(int64_t n);
+size_t gpc_kmap_sparse_workspace_bytes(int64_t n);
+int gpc_kmap_sparse_count(const int32_t *map, int64_t n, uint32_t *seg, uint32_t *rowptr, uint32_t *totals, void *ws,
+                          size_t ws_bytes, void *stream);
+int gpc_kmap_sparse_fill(const int32_t *map, int64_t n, const uint32_t *seg, const uint32_t *rowptr, const void *ws,
+                         uint64_t *pairs, int64_t n_entries, void *stream);
+/* y[o,:] = act( W[centre]^T x[o,:] + sum of the row's stragglers in ascending offset order (+ residual[o,:]) ); fp32 rows in and
+ * out; Wa = this conv's slice of gpc_spconv_pack_weights_frag; contrib = scratch of max(stragglers, 1) * 32 floats */
+int gpc_spconv_sparse_fwd(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs, const uint32_t *rowptr,
+                          int64_t n, int64_t n_entries, float *contrib, const float *residual, int flags, float *y, void *stream);
+
 /* ---- the tcgen05 sparse conv (spconv_tc.cu, spconv_fmt.cu): the kernel the big octree levels run ---- */
 /* "split rows": an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits) -- a gathered
  * row is a tensor-core operand row as it stands */

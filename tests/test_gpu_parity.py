@@ -207,6 +207,49 @@ def test_sparse_conv(env, n, ext):
 
 
 @pytest.fixture(scope="module")
+def env_sparse(env):
+    """A codec whose levels ALL run the centre + stragglers conv (spconv_sparse.cu), whatever their size and density."""
+    from gauspcc_b200.codec import GausPcgcCodec
+    codec = GausPcgcCodec(env["codec"].w, env["dev"])
+    codec.sparse_min_rows, codec.sparse_max_density = 1, 1e9
+    return dict(env, codec=codec)
+
+
+@pytest.mark.parametrize("n,ext", [(30000, 16), (20000, 14), (9000, 6), (700, 4), (33, 3)])
+def test_sparse_conv_centre_stragglers(env_sparse, n, ext):
+    """dense centre product + offset-sorted stragglers against the fp32 oracle conv; several 8192-row blocks, ragged tails,
+    rows without any neighbour and rows with many"""
+    from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
+    from oracle import oracle as O
+    codec, w = env_sparse["codec"], env_sparse["w"]
+    xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
+    xyz = xyz[O.sort_zyx_perm(xyz)]
+    keys, _ = _keys_of(codec, xyz)
+    codec._seen_sparse = True
+    km = codec.build_kmap(keys)
+    assert km.sparse
+    ref_km = O.kmap(xyz, 5)
+    assert km.n_real == int((ref_km >= 0).sum())
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(n, 32)).astype(np.float32)
+    res = rng.normal(size=(n, 32)).astype(np.float32)
+    xd, rd = torch.tensor(x, device=codec.dev), torch.tensor(res, device=codec.dev)
+    ref = O.conv(x, w["target_resnet.2.conv1.kernel"], ref_km)
+    scale = max(np.abs(ref).max(), 1.0)
+    y = codec.conv(xd, 7, km).cpu().numpy()
+    assert np.abs(y - ref).max() <= 3e-5 * scale
+    y2 = codec.conv(xd, 7, km, residual=rd, relu=True).cpu().numpy()
+    assert np.abs(y2 - np.maximum(ref + res, 0)).max() <= 3e-5 * scale
+    assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)            # deterministic
+
+
+@pytest.mark.parametrize("n,seed,ext", [(20000, 1, 16), (2500, 5, 12)])
+def test_codec_sparse_conv_vs_oracle(env_sparse, n, seed, ext):
+    """the whole codec with every level on the centre + stragglers conv: same bars as test_codec_vs_oracle"""
+    test_codec_vs_oracle(env_sparse, n, seed, ext)
+
+
+@pytest.fixture(scope="module")
 def env_umma(env):
     """A second codec whose levels ALL run the tcgen05 conv (split rows), whatever their size and density."""
     from gauspcc_b200.codec import GausPcgcCodec

@@ -24,12 +24,15 @@ def main():
     for variant, tr in configs:
         codec = GausPcgcCodec(w, dev, tile_rows=tr)
         codec.conv_variant = variant
-        if variant >= 100:
+        if variant == 200:                  # centre + stragglers conv on every level
+            codec.conv_variant, codec.sparse_min_rows, codec.sparse_max_density = 42, 1, 1e9
+        elif variant >= 100:
             codec.tc_cta_rows, codec.tc_min_density = tr, 0.0
         tot_ms, tot_pairs = 0.0, 0
         line = []
         for li, lv in enumerate(sel):
             codec.conv_profile = []
+            codec._seen_sparse = variant == 200
             km = codec.build_kmap(lv.keys)
             codec.conv_profile = None
             g = torch.Generator(device=dev).manual_seed(li)
