@@ -126,10 +126,10 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
     if (ntiles == 0) return;
     const u64 *tile_base = pairs + p0;
     const int er = lane & 7, epg = lane >> 3;          // this lane copies row `er` of a tile, 32-byte piece `epg`
-    auto issue_tile = [&](int tile) {
+    auto load_entry = [&](int tile) -> u64 { return tile < ntiles ? __ldg(tile_base + (i64)tile * 8 + er) : ~0ull; };
+    auto issue_tile = [&](int tile, u64 e) {             // entry fetched one tile earlier: the copies do not wait on it
         if (tile < ntiles) {
             const int slot = tile % SP_D;
-            const u64 e = __ldg(tile_base + (i64)tile * 8 + er);
             if ((u32)e != 0xFFFFFFFFu) {
                 const float *src = x + (i64)(u32)e * GPC_C + epg * 8;
                 sp_cp_async16(&s.xs[slot][er][epg * 8], src);
@@ -147,8 +147,9 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
 #pragma unroll
             for (int u = 0; u < 2; ++u) { w1[mt][u] = __ldg(wsrc + (mt * 2 + u) * 32); w2[mt][u] = __ldg(wsrc + (4 + mt * 2 + u) * 32); }
     }
+    u64 e_next = load_entry(0);
 #pragma unroll 1
-    for (int c = 0; c < SP_D; ++c) issue_tile(c);
+    for (int c = 0; c < SP_D; ++c) { const u64 e = e_next; e_next = load_entry(c + 1); issue_tile(c, e); }
 #pragma unroll 1
     for (int c = 0; c < ntiles; ++c) {
         sp_cp_async_wait<SP_D - 1>();                    // one group per issue_tile call: tile c has landed
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
         const float4 xc = *reinterpret_cast<const float4 *>(&s.xs[slot][g][8 * t + 4]);
         const u32 dst_a = s.dst[slot][2 * t], dst_b = s.dst[slot][2 * t + 1];
         __syncwarp();                                    // slot fully read: refill it
-        issue_tile(c + SP_D);
+        { const u64 e = e_next; e_next = load_entry(c + SP_D + 1); issue_tile(c + SP_D, e); }
         u32 xf1[2][2], xf2[2][2];
         split_bf16(xa.x, xa.y, xf1[0][0], xf2[0][0]);
         split_bf16(xa.z, xa.w, xf1[0][1], xf2[0][1]);
@@ -240,40 +241,41 @@ __global__ void __launch_bounds__(128) sp_centre_kernel(const float *__restrict_
         bq[0] = d[0][1]; bq[8] = d[0][3]; bq[16] = d[1][1]; bq[24] = d[1][3];
     }
     __syncwarp();
-    // epilogue: eight lanes per row (16 bytes each), 4 rows per step, two steps in flight: 8 rows' contribution loads overlap
-    // (one row at a time with lane = channel waited for rowptr, then for every contribution: 320 us on the 981 K-row level)
+    // epilogue: eight lanes per row (16 bytes each), 4 rows per warp instruction, SP_H such instructions per step: 16 rows' contribution
+    // loads are in flight together (one row at a time with lane = channel waited for rowptr, then for every contribution: 320 us on
+    // the 981 K-row level; 8 rows in flight: 160 us)
     const bool relu = (flags & GPC_CONV_RELU) != 0;
     const int grp = lane >> 3, j4 = lane & 7;
     const float4 *c4 = reinterpret_cast<const float4 *>(contrib);
+    constexpr int SP_H = 4;
 #pragma unroll 1
-    for (int it = 0; it < SP_ROWS / 8; ++it) {
-        float4 v[2];
-        u32 p[2], pe[2];
-        i64 grow[2];
+    for (int it = 0; it < SP_ROWS / (4 * SP_H); ++it) {
+        float4 v[SP_H];
+        u32 p[SP_H], cnt[SP_H];
+        i64 grow[SP_H];
         u32 cmax = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = it * 8 + h * 4 + grp;                          // row within the tile, 0..63
+        for (int h = 0; h < SP_H; ++h) {
+            const int r = it * 4 * SP_H + h * 4 + grp;                   // row within the tile, 0..63
             const u32 pa = __shfl_sync(0xFFFFFFFFu, rp_a, r & 31), pb = __shfl_sync(0xFFFFFFFFu, rp_b, r & 31);
             const u32 qa = __shfl_sync(0xFFFFFFFFu, rp_a, (r + 1) & 31), qb = __shfl_sync(0xFFFFFFFFu, rp_b, (r + 1) & 31);
             p[h] = r < 32 ? pa : pb;
-            pe[h] = r + 1 < 32 ? qa : (r + 1 < 64 ? qb : rp_c);
+            const u32 pe = r + 1 < 32 ? qa : (r + 1 < 64 ? qb : rp_c);
             grow[h] = r0 + r;
-            if (grow[h] >= n) pe[h] = p[h];
+            cnt[h] = grow[h] < n ? pe - p[h] : 0u;
             v[h] = make_float4(acc[r][j4], acc[r][j4 + 8], acc[r][j4 + 16], acc[r][j4 + 24]);     // the contribution rows' channel order
-            cmax = max(cmax, pe[h] - p[h]);
+            cmax = max(cmax, cnt[h]);
         }
-        cmax = __reduce_max_sync(0xFFFFFFFFu, cmax);
         for (u32 o = 0; o < cmax; ++o) {                                 // ascending offset per row: fixed summation order
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-                if (p[h] + o < pe[h]) {
+            for (int h = 0; h < SP_H; ++h)
+                if (o < cnt[h]) {
                     const float4 c = __ldg(c4 + (size_t)(p[h] + o) * 8 + j4);
                     v[h].x += c.x; v[h].y += c.y; v[h].z += c.z; v[h].w += c.w;
                 }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < SP_H; ++h) {
             if (grow[h] >= n) continue;
             float *yo = y + grow[h] * GPC_C + j4;                        // lane j4 owns channels j4, j4+8, j4+16, j4+24: 32-byte runs
             if (residual) {
