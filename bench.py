@@ -155,11 +155,13 @@ def main():
     x_dev = x_dev[calculate_morton_order(x_dev)]                     # as HAC hands it over (gaussian_model.py:1108-1109)
 
     def step():
+        """one encode + decode; returns only scalars: a step must not keep the previous step's device buffers alive (the caching
+        allocator would cudaMalloc a second and third working set inside the timed region: 149-203 ms per step instead of 135)"""
         bx, bo, _, aux = codec.encode(x_dev, download=False)
         n_enc = codec.launches
         occs = [lv.occ for lv in aux["levels"][1:]]
         out = codec.decode(bx, bo, [b""] * (4 * len(occs)), forced_occ=occs)
-        return out, n_enc + codec.launches, aux
+        return int(out.shape[0]), n_enc + codec.launches, (int(len(aux["levels"]) - 1), int(sum(l.n for l in aux["levels"][1:])))
 
     def barrier():
         if world > 1:
@@ -168,31 +170,34 @@ def main():
 
     codec.conv_profile = []                                          # also makes build_kmap count the true pairs
     for _ in range(args.warmup):
-        out, _, _ = step()
-    assert out.shape[0] == args.points
+        n_out, _, _ = step()
+    assert n_out == args.points
     barrier()
-    codec.prewarm_profile_events(2 * (len(codec.conv_profile) // max(args.warmup, 1) + 8) * args.steps)     # 2 events per conv launch
+    codec.prewarm_profile_events(2 * (len(codec.conv_profile) // max(args.warmup, 1) + 8) * args.steps)     # 2 events per conv group
     sampler = ClockSampler(local)
-    sampler.start()
-    codec.conv_profile = []
+    if not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
+    codec.conv_profile = [] if not os.environ.get("BENCH_NO_PROFILE") else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     t_wall0 = time.perf_counter()
     e0.record(torch.cuda.current_stream(dev))
     for _ in range(args.steps):
-        out, nl, aux = step()
+        n_out, nl, (n_levels, n_symbol_rows) = step()
         launches += nl
     e1.record(torch.cuda.current_stream(dev))
     barrier()
     t_wall = time.perf_counter() - t_wall0
     sampler.stop_flag.set()
-    sampler.join()
+    if sampler.is_alive():
+        sampler.join()
     ms = e0.elapsed_time(e1)
-    prof = codec.conv_profile
+    prof = codec.conv_profile or []
     codec.conv_profile = None
-    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
-    conv_bytes = sum(b for _, _, b, _ in prof)
-    conv_flops = sum(f for _, _, _, f in prof)
+    conv_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
+    conv_bytes = sum(p[2] for p in prof)
+    conv_flops = sum(p[3] for p in prof)
+    conv_launches = sum(p[4] for p in prof)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
@@ -247,8 +252,8 @@ def main():
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"GausPcgc encode/decode, {args.points} synthetic anchors (sparse-global/dense-local HAC++ "
-                                   f"distribution), 1 scene per B200", "points_per_gpu": args.points, "levels": int(len(aux["levels"]) - 1),
-                       "symbol_rows": int(sum(l.n for l in aux["levels"][1:])), "tile_rows": codec.tile_rows,
+                                   f"distribution), 1 scene per B200", "points_per_gpu": args.points, "levels": n_levels,
+                       "symbol_rows": n_symbol_rows, "tile_rows": codec.tile_rows,
                        "l2": "working set (>= 128 MB feature arrays per level) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"scene-sharded x{world}", "wall_ms_per_step": round(t_wall * 1e3 / args.steps, 2)},
             "gpu_launches": int(launches),
@@ -258,9 +263,9 @@ def main():
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                          # dram__bytes_read+write of the profiled launch (442 133-row level) / its algorithmic bytes = 1.003
                          # (profiles/r01_spconv_v6_ncu_summary.md); scaled to the average launch of this run
-                         "traffic": round(1.003 * conv_bytes / max(len(prof), 1)),
+                         "traffic": round(1.003 * conv_bytes / max(conv_launches, 1)),
                          "note": "not HBM-bound: L1/shared path 80.7 %, issue 56 %, HMMA pipe 27 % (ncu); see DESIGN.md 5",
-                         "launches": len(prof), "avg_launch_ms": round(conv_ms / max(len(prof), 1), 4),
+                         "launches": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4), "event_pairs": len(prof),
                          "share_of_step": round(conv_ms / ms, 4), "tflops_fp32": round(conv_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms else 0},
         }
         if e2e:

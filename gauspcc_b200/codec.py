@@ -33,7 +33,8 @@ BASE_ROWS = 64                   # FOG loop stops when a level has < 64 rows (pc
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return C.c_void_p(0 if t is None else t.data_ptr())
+    """device address as a plain int (None = NULL): ctypes converts it for the c_void_p argtypes without an intermediate object"""
+    return None if t is None else t.data_ptr()
 
 
 @dataclass
@@ -120,6 +121,8 @@ class GausPcgcCodec:
         self.sparse_max_density = float(os.environ.get("GPC_SPARSE_MAX_DENSITY", 4.5))
         self.sparse_min_rows = int(os.environ.get("GPC_SPARSE_MIN_ROWS", 150_000))
         self._seen_sparse = False
+        self._fns: Dict[str, object] = {}
+        self._stream_h = None
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
@@ -127,11 +130,17 @@ class GausPcgcCodec:
         self.last_stats: Dict[str, float] = {}
         self._segments: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
         self._seg_open: Optional[torch.cuda.Event] = None
-        self.conv_profile: Optional[list] = None       # bench.py: [(ev0, ev1, algorithmic bytes, flops)] per conv launch
+        self.conv_profile: Optional[list] = None       # bench.py: [(ev0, ev1, algorithmic bytes, flops, launches)] per group of convs
+        self._prof_group = None
+        self._prof_single = None
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        """raw handle of torch's current stream; inside encode() / decode() it is looked up once (the host issues ~1 500 launches per
+        step and must stay ahead of the GPU on the coarse levels, where a kernel is shorter than a careless Python call)"""
+        if self._stream_h is not None:
+            return self._stream_h
+        return torch.cuda.current_stream(self.dev).cuda_stream
 
     def _empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.dev)
@@ -184,8 +193,19 @@ class GausPcgcCodec:
         torch.cuda.synchronize(self.dev)
         self._ev_next = 0
 
+    def _popcount(self, occ: torch.Tensor) -> int:
+        """number of children of a level = set bits of its occupancy bytes, counted on the device (8 B back instead of the level)"""
+        if not hasattr(self, "_pop8"):
+            self._pop8 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int32, device=self.dev)
+        return int(self._pop8[occ.long()].sum().item()) if occ.numel() else 0
+
     def _call(self, name, *args):
-        _lib.check(getattr(self.lib, name)(*args), name)
+        fn = self._fns.get(name)
+        if fn is None:
+            fn = self._fns[name] = getattr(self.lib, name)
+        rc = fn(*args)
+        if rc:
+            _lib.check(rc, name)
 
     @property
     def launches(self) -> int:
@@ -373,27 +393,19 @@ class GausPcgcCodec:
             xs = x if x.dtype == torch.int32 else self.split_rows(x)
             y = (out if out is not None else self._empty((n, 32), torch.float32)) if fmt in ("f32", "both") else None
             ys = self._empty((n, 32), torch.int32) if fmt in ("split", "both") else None
-            if self.conv_profile is not None:
-                e0, e1 = self._profile_events()
-                e0.record(torch.cuda.current_stream(self.dev))
+            self._prof_conv_begin()
             flags = (1 if relu else 0) | (2 if (residual is not None and residual.dtype == torch.int32) else 0)
             self._call("gpc_spconv_fwd_tc", _ptr(xs), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.cta_rows,
                        _ptr(residual), flags, _ptr(y), _ptr(ys), 1 if self.conv_variant == 101 else 0, self._stream())
-            if self.conv_profile is not None:
-                e1.record(torch.cuda.current_stream(self.dev))
-                self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
+            self._prof_conv_end(n, km)
             return y if fmt == "f32" else (ys if fmt == "split" else (y, ys))
         assert fmt == "f32" and x.dtype == torch.float32
         y = out if out is not None else self._empty((n, 32), torch.float32)
-        if self.conv_profile is not None:
-            e0, e1 = self._profile_events()
-            e0.record(torch.cuda.current_stream(self.dev))
+        self._prof_conv_begin()
         if km.sparse:
             self._call("gpc_spconv_sparse_fwd", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), _ptr(km.rowptr), n,
                        km.n_pairs, _ptr(km.contrib), _ptr(residual), 1 if relu else 0, _ptr(y), self._stream())
-            if self.conv_profile is not None:
-                e1.record(torch.cuda.current_stream(self.dev))
-                self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
+            self._prof_conv_end(n, km)
             return y
         wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
         if self.conv_variant >= 100 or self.conv_variant == 42:
@@ -420,14 +432,49 @@ class GausPcgcCodec:
         else:
             self._call("gpc_spconv_fwd", _ptr(x), _ptr(wt), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_row), n,
                        km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
-        if self.conv_profile is not None:
-            e1.record(torch.cuda.current_stream(self.dev))
-            # SURVEY.md 8(d): per layer n*C*4*2 + pairs*8 + K^3*C^2*4 bytes and 2*pairs*C^2 FLOP
-            self.conv_profile.append((e0, e1, n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4, 2 * km.n_real * 32 * 32))
+        self._prof_conv_end(n, km)
         return y
+
+    # ---- bench.py's conv timing.  One CUDA-event pair per GROUP of convs on the same level (a 5-conv stack, a 2-conv stage):
+    # an event pair around every conv launch (936 records per step) cost 10-50 ms per step and made the step time jitter
+    # (tools/jitter.py: 134.6 +- 0.1 ms unprofiled against 146-185 ms with per-conv events).
+    def _prof_open(self):
+        if self.conv_profile is None or self._prof_group is not None:
+            return None
+        e0, e1 = self._profile_events()
+        e0.record(torch.cuda.current_stream(self.dev))
+        self._prof_group = [e0, e1, 0, 0, 0]
+        return self._prof_group
+
+    def _prof_close(self, grp):
+        if grp is None:
+            return
+        grp[1].record(torch.cuda.current_stream(self.dev))
+        self.conv_profile.append(tuple(grp))
+        self._prof_group = None
+
+    def _prof_conv_begin(self):
+        self._prof_single = self._prof_open()          # None inside a group (or when not profiling)
+
+    def _prof_conv_end(self, n: int, km: KMap):
+        g = self._prof_group
+        if g is not None:
+            # SURVEY.md 8(d): per layer n*C*4*2 + pairs*8 + K^3*C^2*4 bytes and 2*pairs*C^2 FLOP
+            g[2] += n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4
+            g[3] += 2 * km.n_real * 32 * 32
+            g[4] += 1
+        self._prof_close(self._prof_single)
+        self._prof_single = None
 
     def res_stack(self, x: torch.Tensor, ids, km: KMap, final: str = "f32"):
         """Conv3d, ReLU, ResNet, ResNet (network_ue_4stage_conv.py:17-22; ResNet kit/nn.py:18-22)."""
+        grp = self._prof_open()
+        try:
+            return self._res_stack(x, ids, km, final)
+        finally:
+            self._prof_close(grp)
+
+    def _res_stack(self, x: torch.Tensor, ids, km: KMap, final: str):
         if km.cta_rows:            # tcgen05 level: everything between the first and the last conv stays in split rows
             x = self.conv(x, ids[0], km, relu=True, fmt="split")
             t = self.conv(x, ids[1], km, relu=True, fmt="split")
@@ -470,8 +517,10 @@ class GausPcgcCodec:
             self._call("gpc_add_ctx_embed", _ptr(u), _ptr(occ_partial), CTX_SHIFT[i], _ptr(self.w.stage_emb[i]), n, _ptr(f),
                        self._stream())
         c0, c1 = W.stage_convs(i)
+        grp = self._prof_open()
         t = self.conv(f, c0, km, relu=True, fmt="split" if km.cta_rows else "f32")
         t = self.conv(t, c1, km)
+        self._prof_close(grp)
         w1, b1, w2, b2 = self.w.head[i]
         if lohi_out is not None:
             self._call("gpc_head_cdf_sym", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(occ_partial),
@@ -517,6 +566,7 @@ class GausPcgcCodec:
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
         self._seen_sparse = False
+        self._stream_h = torch.cuda.current_stream(self.dev).cuda_stream
         self._seg_begin()
         xyz = xyz.contiguous()
         keys, meta = self.pack_keys(xyz)
@@ -575,6 +625,7 @@ class GausPcgcCodec:
         self._seg_end()
         gpu_ms = self._seg_total_ms()                  # synchronises: all D2H copies have landed
         streams = [f.result() for f in futs] if download else None
+        self._stream_h = None
         self.last_stats = {"gpu_ms": gpu_ms, "launches": self.launches, "rows": rows, "levels": L,
                            "d2h_bytes": cursor, "n_unique": int(leaf.shape[0])}
         return base_xyz_h, base_occ_h, streams, aux
@@ -592,6 +643,7 @@ class GausPcgcCodec:
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
         self._seen_sparse = False
+        self._stream_h = torch.cuda.current_stream(self.dev).cuda_stream
         if len(streams) % 4:
             raise ValueError("stream count must be a multiple of 4 (one group per octree level)")
         self._seg_begin()
@@ -613,7 +665,7 @@ class GausPcgcCodec:
         pin = None
         t_wait = t_ac = 0.0
         for g in range(0, len(streams), 4):
-            n_child = int(np.unpackbits(cur.occ.cpu().numpy()).sum()) if forced_occ is None else int(forced_occ[g // 4].shape[0])
+            n_child = self._popcount(cur.occ) if forced_occ is None else int(forced_occ[g // 4].shape[0])
             child, u = self.level_features(cur, n_child)
             occ = torch.zeros(n_child, dtype=torch.uint8, device=self.dev)
             if pin is None or pin.numel() < n_child * 40:
@@ -642,7 +694,7 @@ class GausPcgcCodec:
                 self._call("gpc_merge_symbol", _ptr(occ), n_child, STAGE_SHIFT[i], _ptr(sym_d), self._stream())
             child.occ = occ
             cur = child
-        n_pts = int(np.unpackbits(cur.occ.cpu().numpy()).sum())
+        n_pts = self._popcount(cur.occ)
         out = self._empty((n_pts, 3), torch.float32)
         if sorted_rows:
             ck, _ = self.expand(cur, n_pts)            # child keys already in (z,y,x) order: closed-form ranks, no sort
@@ -653,6 +705,7 @@ class GausPcgcCodec:
             self._call("gpc_expand_leaves_f32", _ptr(cur.keys), _ptr(cur.occ), cur.n, n_pts, float(scale), _ptr(out), _ptr(ws), ws_b,
                        self._stream())
         self._seg_end()
+        self._stream_h = None
         self.last_stats = {"gpu_ms": self._seg_total_ms(), "launches": self.launches, "host_ac_s": t_ac, "gpu_wait_s": t_wait}
         return out
 
