@@ -284,7 +284,7 @@ class GausPcgcCodec:
     def _v6_config(self, n: int) -> Tuple[int, int]:
         """(rows per CTA, kernel variant) of the mma.sync conv for a level of n rows (tools/conv_ab.py, AB_MIN_ROWS=50):
         64 rows per warp on big levels (W^T reuse); fewer rows on the coarse levels so that they still fill the 148 SMs; on the
-        coarsest levels the 125 offsets of a tile are additionally split over 2 / 8 / 16 warps (variants 45 / 46 / 47): those
+        coarse levels the 125 offsets of a tile are additionally split over 4 / 8 / 16 warps (variants 44 / 46 / 47): those
         launches are bound by one warp's chain of dependent 8-pair tiles, ~63 us each before, 15-30 us now."""
         if self.conv_variant < 100 and (self.conv_variant != 42 or not self.adaptive_tiles):
             return self.tile_rows, self.conv_variant
@@ -293,9 +293,9 @@ class GausPcgcCodec:
         if n >= 150_000:
             return 64, 42
         if n >= 40_000:
-            return 32, 45
+            return 64, 44
         if n >= 20_000:
-            return 16, 42
+            return 32, 46
         if n >= 1_500:
             return 16, 46
         return 8, 47

@@ -1236,9 +1236,11 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
         if (tile_rows == 16) return launch_spconv_v6<16, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
         if (tile_rows == 32) return launch_spconv_v6<32, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 64) return launch_spconv_v6<64, 4, 4>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 46) {          // split offsets over 8 warps
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
         if (tile_rows == 16) return launch_spconv_v6<16, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
+        if (tile_rows == 32) return launch_spconv_v6<32, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 47) {          // split offsets over 16 warps
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 16>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 45) {          // split offsets over 2 warps
