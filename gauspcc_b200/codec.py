@@ -357,7 +357,8 @@ class GausPcgcCodec:
             self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
             return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
         km = None
-        sparse_ok = self.conv_variant in (42, 100) and self.sparse_max_density > 0 and not keep_dense and n >= self.sparse_min_rows
+        sparse_ok = (self.conv_variant in (42, 100) and self.sparse_max_density > 0 and not keep_dense
+                     and self.sparse_min_rows <= n < 30_000_000)         # 32-bit straggler indices: n * 124 < 2^32
         if sparse_ok and self._seen_sparse:
             return self._sparse_map(dense, n)
         if self.conv_variant >= 100 and not keep_dense and n >= self.tc_min_rows:
