@@ -104,41 +104,36 @@ __global__ void __launch_bounds__(128) sp_fill_kernel(const i32 *__restrict__ ma
 }
 
 // ---------------------------------------------------------------- kernel 1: stragglers, one warp per (block, offset) segment
-constexpr int SP_D = 4;            // gather ring depth (8-pair tiles)
-constexpr int SP_XS = 36;
-struct SpSmem1 {
-    float xs[SP_D][8][SP_XS];
-    u32 dst[SP_D][8];
-};
-
+// No shared memory: lane (g, t) of an 8-pair MMA tile needs exactly 32 contiguous bytes of pair g's row (channels 8t .. 8t+7 in the
+// fragment order of gpc_spconv_pack_weights_frag), so the four lanes of a quad read one 128 B row straight into the B fragments
+// (2 x LDG.128 per lane).  Entries are fetched 32 at a time (4 tiles, one coalesced 256 B load) and handed out by shuffles; the rows
+// of tile T + 2 are requested before tile T is multiplied (four register slots, indexed statically by the unrolled loop).
 __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
                                                            const u32 *__restrict__ seg, const u64 *__restrict__ pairs, i64 n_seg,
-                                                           float *__restrict__ contrib) {
-    __shared__ SpSmem1 smem[4];
-    SpSmem1 &s = smem[threadIdx.x >> 5];
+                                                           int SP_SPLIT, float *__restrict__ contrib) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const i64 i = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    // SP_SPLIT warps per segment (chosen by the host from the average segment length): the segments of the offsets next to the
+    // centre are 10-50 x longer than the rest; a long one (>= 8 tiles per part) is cut into up to SP_SPLIT tile ranges so that the
+    // tail of the launch is not a few warps deep.  Levels with short segments launch one warp per segment.
+    const i64 wg = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const i64 i = wg / SP_SPLIT;
+    const int part = (int)(wg % SP_SPLIT);
     if (i >= n_seg) return;
     const i64 b = i / SP_KK;
     const int kk = (int)(i % SP_KK);
-    const u32 p0 = __ldg(seg + b * GPC_K3 + kk);
-    const int ntiles = (int)((__ldg(seg + b * GPC_K3 + kk + 1) - p0) >> 3);
+    const u32 p00 = __ldg(seg + b * GPC_K3 + kk);
+    const int ntiles_seg = (int)((__ldg(seg + b * GPC_K3 + kk + 1) - p00) >> 3);
+    const int nparts = min(SP_SPLIT, (ntiles_seg + 7) / 8);
+    if (part >= nparts) return;
+    const int t_begin = (int)((i64)ntiles_seg * part / nparts), t_end = (int)((i64)ntiles_seg * (part + 1) / nparts);
+    const int ntiles = t_end - t_begin;
     if (ntiles == 0) return;
-    const u64 *tile_base = pairs + p0;
-    const int er = lane & 7, epg = lane >> 3;          // this lane copies row `er` of a tile, 32-byte piece `epg`
-    auto load_entry = [&](int tile) -> u64 { return tile < ntiles ? __ldg(tile_base + (i64)tile * 8 + er) : ~0ull; };
-    auto issue_tile = [&](int tile, u64 e) {             // entry fetched one tile earlier: the copies do not wait on it
-        if (tile < ntiles) {
-            const int slot = tile % SP_D;
-            if ((u32)e != 0xFFFFFFFFu) {
-                const float *src = x + (i64)(u32)e * GPC_C + epg * 8;
-                sp_cp_async16(&s.xs[slot][er][epg * 8], src);
-                sp_cp_async16(&s.xs[slot][er][epg * 8 + 4], src + 4);
-            }
-            if (lane < 8) s.dst[slot][lane] = (u32)(e >> 32);
-        }
-        sp_cp_async_commit();
+    const u64 *tile_base = pairs + p00 + (size_t)t_begin * 8;
+    auto load_bulk = [&](int k) -> u64 {                 // lane l: entry (tile 4k + l / 8, pair l % 8)
+        const int e = k * 32 + lane;
+        return e < ntiles * 8 ? __ldg(tile_base + e) : ~0ull;
     };
+    u64 eb0 = load_bulk(0), eb1 = load_bulk(1);
     uint4 w1[2][2], w2[2][2];                            // A fragments of W^T[k] (bf16 hi / lo), [mt][u]: once per segment
     {
         const uint4 *wsrc = Wa + (size_t)sp_offset(kk) * 256 + lane;
@@ -147,41 +142,52 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
 #pragma unroll
             for (int u = 0; u < 2; ++u) { w1[mt][u] = __ldg(wsrc + (mt * 2 + u) * 32); w2[mt][u] = __ldg(wsrc + (4 + mt * 2 + u) * 32); }
     }
-    u64 e_next = load_entry(0);
+    float4 xa[4], xc[4];
+    u32 dsa[4], dsb[4];
+    auto issue = [&](float4 &a, float4 &c, u32 &da, u32 &db, u64 eb, int tl) {      // rows + destinations of tile `tl` of the bulk in eb
+        const u32 nb = __shfl_sync(0xFFFFFFFFu, (u32)eb, tl * 8 + g);
+        const u32 hi = (u32)(eb >> 32);
+        da = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t);
+        db = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t + 1);
+        a = make_float4(0.f, 0.f, 0.f, 0.f); c = a;
+        if (nb != 0xFFFFFFFFu) {
+            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)nb * GPC_C + 8 * t);
+            a = __ldg(src); c = __ldg(src + 1);
+        }
+    };
+    issue(xa[0], xc[0], dsa[0], dsb[0], eb0, 0);
+    if (ntiles > 1) issue(xa[1], xc[1], dsa[1], dsb[1], eb0, 1);
 #pragma unroll 1
-    for (int c = 0; c < SP_D; ++c) { const u64 e = e_next; e_next = load_entry(c + 1); issue_tile(c, e); }
-#pragma unroll 1
-    for (int c = 0; c < ntiles; ++c) {
-        sp_cp_async_wait<SP_D - 1>();                    // one group per issue_tile call: tile c has landed
-        __syncwarp();
-        const int slot = c % SP_D;
-        const float4 xa = *reinterpret_cast<const float4 *>(&s.xs[slot][g][8 * t]);
-        const float4 xc = *reinterpret_cast<const float4 *>(&s.xs[slot][g][8 * t + 4]);
-        const u32 dst_a = s.dst[slot][2 * t], dst_b = s.dst[slot][2 * t + 1];
-        __syncwarp();                                    // slot fully read: refill it
-        { const u64 e = e_next; e_next = load_entry(c + SP_D + 1); issue_tile(c + SP_D, e); }
-        u32 xf1[2][2], xf2[2][2];
-        split_bf16(xa.x, xa.y, xf1[0][0], xf2[0][0]);
-        split_bf16(xa.z, xa.w, xf1[0][1], xf2[0][1]);
-        split_bf16(xc.x, xc.y, xf1[1][0], xf2[1][0]);
-        split_bf16(xc.z, xc.w, xf1[1][1], xf2[1][1]);
-        float d[2][4];
+    for (int k = 0; 4 * k < ntiles; ++k) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) { d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f; }
+        for (int u = 0; u < 4; ++u) {
+            const int T = 4 * k + u;
+            if (T >= ntiles) break;
+            if (T + 2 < ntiles) issue(xa[(u + 2) & 3], xc[(u + 2) & 3], dsa[(u + 2) & 3], dsb[(u + 2) & 3], u < 2 ? eb0 : eb1, (u + 2) & 3);
+            u32 xf1[2][2], xf2[2][2];
+            split_bf16(xa[u].x, xa[u].y, xf1[0][0], xf2[0][0]);
+            split_bf16(xa[u].z, xa[u].w, xf1[0][1], xf2[0][1]);
+            split_bf16(xc[u].x, xc[u].y, xf1[1][0], xf2[1][0]);
+            split_bf16(xc[u].z, xc[u].w, xf1[1][1], xf2[1][1]);
+            float d[2][4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+            for (int mt = 0; mt < 2; ++mt) { d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f; }
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                sp_mma(d[mt], w1[mt][u], xf2[u][0], xf2[u][1]);
-                sp_mma(d[mt], w2[mt][u], xf1[u][0], xf1[u][1]);
-                sp_mma(d[mt], w1[mt][u], xf1[u][0], xf1[u][1]);
-            }
-        // d[mt][0] = (co 16mt+g, pair 2t), [1] = (co, pair 2t+1), [2]/[3] = co+8.  A contribution row is stored PERMUTED: float4 g
-        // = channels (g, g+8, g+16, g+24), i.e. exactly what lane g holds -> one 16-byte store per pair, 128 contiguous bytes per row
-        if (dst_a != 0xFFFFFFFFu) reinterpret_cast<float4 *>(contrib)[(size_t)dst_a * 8 + g] = make_float4(d[0][0], d[0][2], d[1][0], d[1][2]);
-        if (dst_b != 0xFFFFFFFFu) reinterpret_cast<float4 *>(contrib)[(size_t)dst_b * 8 + g] = make_float4(d[0][1], d[0][3], d[1][1], d[1][3]);
+            for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    sp_mma(d[mt], w1[mt][uu], xf2[uu][0], xf2[uu][1]);
+                    sp_mma(d[mt], w2[mt][uu], xf1[uu][0], xf1[uu][1]);
+                    sp_mma(d[mt], w1[mt][uu], xf1[uu][0], xf1[uu][1]);
+                }
+            // d[mt][0] = (co 16mt+g, pair 2t), [1] = (co, pair 2t+1), [2]/[3] = co+8.  A contribution row is stored PERMUTED: float4 g
+            // = channels (g, g+8, g+16, g+24), i.e. exactly what lane g holds -> one 16-byte store per pair, 128 contiguous bytes per row
+            if (dsa[u] != 0xFFFFFFFFu) reinterpret_cast<float4 *>(contrib)[(size_t)dsa[u] * 8 + g] = make_float4(d[0][0], d[0][2], d[1][0], d[1][2]);
+            if (dsb[u] != 0xFFFFFFFFu) reinterpret_cast<float4 *>(contrib)[(size_t)dsb[u] * 8 + g] = make_float4(d[0][1], d[0][3], d[1][1], d[1][3]);
+        }
+        eb0 = eb1;
+        eb1 = load_bulk(k + 2);
     }
-    sp_cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------- kernel 2: dense centre product + the rows' contributions
@@ -360,7 +366,8 @@ extern "C" int gpc_spconv_sparse_fwd(const float *x, const void *Wa, const uint3
     cudaStream_t st = as_stream(stream);
     const i64 nb = (n + SP_TB - 1) / SP_TB, n_seg = nb * SP_KK;
     if (n_entries > 0) {
-        sp_straggler_kernel<<<cdiv(n_seg, 4), 128, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n_seg, contrib);
+        const int split = n_entries >= 256 * n_seg ? 8 : (n_entries >= 64 * n_seg ? 4 : 1);
+        sp_straggler_kernel<<<cdiv(n_seg * split, 4), 128, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n_seg, split, contrib);
         GPC_LAUNCH_CHECK();
     }
     sp_centre_kernel<<<cdiv(n, 4 * SP_ROWS), 128, 0, st>>>(x, (const uint4 *)Wa, rowptr, contrib, n, residual, flags, y);
