@@ -372,6 +372,8 @@ class GausPcgcCodec:
             tr, v6v = self._v6_config(n)
             km = self._pair_stream(dense, n, tr, pad, self.conv_variant < 10 or keep_dense)
             km.v6_variant = v6v
+            if v6v == 42 and tr == 64 and km.n_real >= 18 * n:
+                km.v6_variant = 48          # densest big levels: rows straight into the MMA fragments (v6d; same sums bit for bit)
             if sparse_ok and km.n_real < self.sparse_max_density * n:
                 self._seen_sparse = True
                 return self._sparse_map(dense, n)

@@ -1195,6 +1195,125 @@ __global__ void __launch_bounds__(32 * G) spconv_fwd_v6_kernel(const float *__re
     }
 }
 
+// ---- v6d: v6 without the shared-memory gather ring.  Lane (g, t) of an 8-pair tile needs exactly the 32 contiguous bytes
+// [8t, 8t+8) of pair g's row, so the four lanes of a quad read one 128 B row straight into the B fragments (2 x LDG.128 per lane):
+// no cp.async, no staging, no LDS, no wait_group / syncwarp per tile.  Entries come 32 at a time (4 tiles, one coalesced 256 B load)
+// and are handed out by shuffles; the rows of tile T + 3 are requested before tile T is multiplied (four register slots indexed
+// statically by the unrolled loop), W^T[k] of tile T + 1 while tile T is multiplied.  Accumulators and their fixed order as in v6.
+template <int TW>
+__global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
+                                                            const u32 *__restrict__ seg_g, const u64 *__restrict__ pairs, i64 n,
+                                                            const float *__restrict__ residual, int flags, float *__restrict__ y) {
+    __shared__ float acc[TW][SC6_ACC];
+    const int lane = threadIdx.x;
+    const int g = lane >> 2, t = lane & 3;
+    const i64 st = blockIdx.x;
+    const i64 r0 = st * TW;
+    const int rows = (int)min((i64)TW, n - r0);
+    const u32 p_begin = __ldg(seg_g + st * (GPC_K3 + 1));
+    const int ntiles = (int)((__ldg(seg_g + st * (GPC_K3 + 1) + GPC_K3) - p_begin) >> 3);
+    const u64 *tile_base = pairs + p_begin;
+    for (int i = lane; i < TW * SC6_ACC / 4; i += 32) reinterpret_cast<float4 *>(&acc[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    auto load_bulk = [&](int k) -> u64 {                 // lane l: entry (tile 4k + l / 8, pair l % 8)
+        const int e = k * 32 + lane;
+        return e < ntiles * 8 ? __ldg(tile_base + e) : ~0ull;
+    };
+    u64 eb0 = load_bulk(0), eb1 = load_bulk(1);
+    float4 xa[4], xc[4];
+    u32 rwa[4], rwb[4], kof[4];
+    auto issue = [&](float4 &a, float4 &c, u32 &ra, u32 &rb, u32 &kk, u64 eb, int tl) {
+        const u32 nb = __shfl_sync(0xFFFFFFFFu, (u32)eb, tl * 8 + g);
+        const u32 hi = (u32)(eb >> 32);
+        ra = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t) & 0xFFFFu;               // padding entries: 0xFFFF
+        rb = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t + 1) & 0xFFFFu;
+        kk = __shfl_sync(0xFFFFFFFFu, hi, tl * 8) >> 16;                           // entry 0 of a tile is always a real pair
+        a = make_float4(0.f, 0.f, 0.f, 0.f); c = a;
+        if (nb != 0xFFFFFFFFu) {
+            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)nb * GPC_C + 8 * t);
+            a = __ldg(src); c = __ldg(src + 1);
+        }
+    };
+    auto load_w = [&](uint4 (&a1)[2][2], uint4 (&a2)[2][2], u32 k) {
+        const uint4 *wsrc = Wa + (size_t)k * 256 + lane;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { a1[mt][u] = __ldg(wsrc + (mt * 2 + u) * 32); a2[mt][u] = __ldg(wsrc + (4 + mt * 2 + u) * 32); }
+    };
+    uint4 w1[2][2], w2[2][2];
+    u32 k_cur = 0xFFFFFFFFu;
+    if (ntiles > 0) {
+        issue(xa[0], xc[0], rwa[0], rwb[0], kof[0], eb0, 0);
+        if (ntiles > 1) issue(xa[1], xc[1], rwa[1], rwb[1], kof[1], eb0, 1);
+        if (ntiles > 2) issue(xa[2], xc[2], rwa[2], rwb[2], kof[2], eb0, 2);
+        k_cur = kof[0];
+        load_w(w1, w2, k_cur);
+    }
+#pragma unroll 1
+    for (int kb = 0; 4 * kb < ntiles; ++kb) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int T = 4 * kb + u;
+            if (T >= ntiles) break;
+            // tile T - 1's slot is free: its fragments were converted and its rows / offset consumed in the previous step
+            if (T + 3 < ntiles)
+                issue(xa[(u + 3) & 3], xc[(u + 3) & 3], rwa[(u + 3) & 3], rwb[(u + 3) & 3], kof[(u + 3) & 3], u < 1 ? eb0 : eb1, (u + 3) & 3);
+            // W of the next tile if its offset differs (warp-uniform): in flight during this tile's MMAs
+            const u32 k_next = T + 1 < ntiles ? kof[(u + 1) & 3] : k_cur;
+            const bool newk = k_next != k_cur;
+            uint4 n1[2][2], n2[2][2];
+            if (newk) load_w(n1, n2, k_next);
+            u32 xf1[2][2], xf2[2][2];
+            split_bf16(xa[u].x, xa[u].y, xf1[0][0], xf2[0][0]);
+            split_bf16(xa[u].z, xa[u].w, xf1[0][1], xf2[0][1]);
+            split_bf16(xc[u].x, xc[u].y, xf1[1][0], xf2[1][0]);
+            split_bf16(xc[u].z, xc[u].w, xf1[1][1], xf2[1][1]);
+            float d[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f; }
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_bf16_a4(d[mt], w1[mt][uu], xf2[uu][0], xf2[uu][1]);
+                    mma_bf16_a4(d[mt], w2[mt][uu], xf1[uu][0], xf1[uu][1]);
+                    mma_bf16_a4(d[mt], w1[mt][uu], xf1[uu][0], xf1[uu][1]);
+                }
+            {   // scatter-add: the two pairs of a lane are different rows; all loads before the first store
+                const u32 row_a = rwa[u], row_b = rwb[u];
+                const bool va = row_a != 0xFFFFu, vb = row_b != 0xFFFFu;
+                float *pa = &acc[va ? row_a : 0u][g], *pb = &acc[vb ? row_b : 0u][g];
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                if (va) { a0 = pa[0]; a1 = pa[8]; a2 = pa[16]; a3 = pa[24]; }
+                if (vb) { b0 = pb[0]; b1 = pb[8]; b2 = pb[16]; b3 = pb[24]; }
+                a0 += d[0][0]; a1 += d[0][2]; a2 += d[1][0]; a3 += d[1][2];
+                b0 += d[0][1]; b1 += d[0][3]; b2 += d[1][1]; b3 += d[1][3];
+                if (va) { pa[0] = a0; pa[8] = a1; pa[16] = a2; pa[24] = a3; }
+                if (vb) { pb[0] = b0; pb[8] = b1; pb[16] = b2; pb[24] = b3; }
+            }
+            __syncwarp();                                // the next tile may touch the same accumulator rows from other lanes
+            if (newk) {
+                k_cur = k_next;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int uu = 0; uu < 2; ++uu) { w1[mt][uu] = n1[mt][uu]; w2[mt][uu] = n2[mt][uu]; }
+            }
+        }
+        eb0 = eb1;
+        eb1 = load_bulk(kb + 2);
+    }
+    __syncwarp();
+    const bool relu = (flags & GPC_CONV_RELU) != 0;
+    for (int r = 0; r < rows; ++r) {
+        float v = acc[r][lane];
+        if (residual) v += __ldg(residual + (r0 + r) * GPC_C + lane);
+        if (relu) v = fmaxf(v, 0.f);
+        y[(r0 + r) * GPC_C + lane] = v;
+    }
+}
+
 template <int TW, int D, int G = 1>
 static int launch_spconv_v6(const float *x, const void *Wa, const u32 *seg, const u64 *pairs, i64 n, const float *residual,
                             int flags, float *y, cudaStream_t st) {
@@ -1241,6 +1360,10 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
         if (tile_rows == 16) return launch_spconv_v6<16, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
         if (tile_rows == 32) return launch_spconv_v6<32, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
+    } else if (variant == 48) {          // v6d: rows straight into the MMA fragments (no shared-memory gather ring)
+        const i64 tiles = (n + tile_rows - 1) / tile_rows;
+        if (tile_rows == 64) { spconv_fwd_v6d_kernel<64><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
+        if (tile_rows == 32) { spconv_fwd_v6d_kernel<32><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
     } else if (variant == 47) {          // split offsets over 16 warps
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 16>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 45) {          // split offsets over 2 warps
