@@ -291,7 +291,7 @@ class GausPcgcCodec:
         if not self.adaptive_tiles:
             return 64, 42
         if n >= 150_000:
-            return 64, 42
+            return 128, 48          # v6d: rows straight into the MMA fragments, 128-row tiles halve the W^T traffic per pair
         if n >= 40_000:
             return 64, 44
         if n >= 20_000:
@@ -372,8 +372,6 @@ class GausPcgcCodec:
             tr, v6v = self._v6_config(n)
             km = self._pair_stream(dense, n, tr, pad, self.conv_variant < 10 or keep_dense)
             km.v6_variant = v6v
-            if v6v == 42 and tr == 64 and km.n_real >= 18 * n:
-                km.v6_variant = 48          # densest big levels: rows straight into the MMA fragments (v6d; same sums bit for bit)
             if sparse_ok and km.n_real < self.sparse_max_density * n:
                 self._seen_sparse = True
                 return self._sparse_map(dense, n)

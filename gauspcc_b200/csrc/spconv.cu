@@ -1219,7 +1219,7 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
         const int e = k * 32 + lane;
         return e < ntiles * 8 ? __ldg(tile_base + e) : ~0ull;
     };
-    u64 eb0 = load_bulk(0), eb1 = load_bulk(1);
+    u64 eb[2] = {load_bulk(0), load_bulk(1)};   // bulks 2j / 2j + 1: statically indexed (a register hand-over would wait for every load in flight)
     float4 xa[4], xc[4];
     u32 rwa[4], rwb[4], kof[4];
     auto issue = [&](float4 &a, float4 &c, u32 &ra, u32 &rb, u32 &kk, u64 eb, int tl) {
@@ -1244,21 +1244,22 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
     uint4 w1[2][2], w2[2][2];
     u32 k_cur = 0xFFFFFFFFu;
     if (ntiles > 0) {
-        issue(xa[0], xc[0], rwa[0], rwb[0], kof[0], eb0, 0);
-        if (ntiles > 1) issue(xa[1], xc[1], rwa[1], rwb[1], kof[1], eb0, 1);
-        if (ntiles > 2) issue(xa[2], xc[2], rwa[2], rwb[2], kof[2], eb0, 2);
+        issue(xa[0], xc[0], rwa[0], rwb[0], kof[0], eb[0], 0);
+        if (ntiles > 1) issue(xa[1], xc[1], rwa[1], rwb[1], kof[1], eb[0], 1);
+        if (ntiles > 2) issue(xa[2], xc[2], rwa[2], rwb[2], kof[2], eb[0], 2);
         k_cur = kof[0];
         load_w(w1, w2, k_cur);
     }
 #pragma unroll 1
-    for (int kb = 0; 4 * kb < ntiles; ++kb) {
+    for (int kb = 0; 8 * kb < ntiles; ++kb) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int T = 4 * kb + u;
+        for (int u8 = 0; u8 < 8; ++u8) {
+            const int u = u8 & 3, h = u8 >> 2;
+            const int T = 8 * kb + u8;
             if (T >= ntiles) break;
             // tile T - 1's slot is free: its fragments were converted and its rows / offset consumed in the previous step
             if (T + 3 < ntiles)
-                issue(xa[(u + 3) & 3], xc[(u + 3) & 3], rwa[(u + 3) & 3], rwb[(u + 3) & 3], kof[(u + 3) & 3], u < 1 ? eb0 : eb1, (u + 3) & 3);
+                issue(xa[(u + 3) & 3], xc[(u + 3) & 3], rwa[(u + 3) & 3], rwb[(u + 3) & 3], kof[(u + 3) & 3], u < 1 ? eb[h] : eb[h ^ 1], (u + 3) & 3);
             // W of the next tile if its offset differs (warp-uniform): in flight during this tile's MMAs
             const u32 k_next = T + 1 < ntiles ? kof[(u + 1) & 3] : k_cur;
             const bool newk = k_next != k_cur;
@@ -1300,9 +1301,8 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
 #pragma unroll
                     for (int uu = 0; uu < 2; ++uu) { w1[mt][uu] = n1[mt][uu]; w2[mt][uu] = n2[mt][uu]; }
             }
+            if (u == 3) eb[h] = load_bulk(2 * kb + h + 2);      // this bulk's last tile is done, tiles T + 1 .. T + 3 come from the other one
         }
-        eb0 = eb1;
-        eb1 = load_bulk(kb + 2);
     }
     __syncwarp();
     const bool relu = (flags & GPC_CONV_RELU) != 0;
@@ -1364,6 +1364,7 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
         const i64 tiles = (n + tile_rows - 1) / tile_rows;
         if (tile_rows == 64) { spconv_fwd_v6d_kernel<64><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
         if (tile_rows == 32) { spconv_fwd_v6d_kernel<32><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
+        if (tile_rows == 128) { spconv_fwd_v6d_kernel<128><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
     } else if (variant == 47) {          // split offsets over 16 warps
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 16>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 45) {          // split offsets over 2 warps
