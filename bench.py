@@ -258,15 +258,16 @@ def main():
                        "parallelism": f"scene-sharded x{world}", "wall_ms_per_step": round(t_wall * 1e3 / args.steps, 2)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": ("spconv_fwd_v6 (mma.sync)" if codec.conv_variant < 100 else "spconv_tc (tcgen05) + spconv_fwd_v6") +
+            "roofline": {"kernel": ("spconv_fwd_v6d / v6 (mma.sync)" if codec.conv_variant < 100 else "spconv_tc (tcgen05) + spconv_fwd_v6") +
                                    " + sp_centre / sp_straggler on the sparse big levels, variant %d" % codec.conv_variant,
                          "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-                         # dram__bytes_read+write of the profiled launch (442 133-row level) / its algorithmic bytes = 1.003
-                         # (profiles/r01_spconv_v6_ncu_summary.md); scaled to the average launch of this run
-                         "traffic": round(1.003 * conv_bytes / max(conv_launches, 1)),
-                         "note": "all sparse-conv launches of the step; the dominant kernel (spconv_fwd_v6<64,4,1>, 58 % of the step) is not HBM-bound: "
-                                 "L1/shared path 80.7 %, issue 56 %, HMMA pipe 27 % (ncu); see DESIGN.md 5",
+                         # dram__bytes_read+write of the profiled launch (442 133-row level, spconv_fwd_v6d<128>: 145.4 + 31.4 MB) / its
+                         # algorithmic bytes (187.9 MB) = 0.94 (profiles/r01_spconv_v6_ncu_summary.md); scaled to the average launch of this run
+                         "traffic": round(0.94 * conv_bytes / max(conv_launches, 1)),
+                         "note": "all sparse-conv launches of the step; the dominant kernel (spconv_fwd_v6d<128>, 56 % of the step) is not HBM-bound: "
+                                 "L1/shared path 59 %, issue 36 %, HMMA pipe 27 %, 10 of 12 resident warps per SM waiting on L2 latency (ncu); "
+                                 "see DESIGN.md 5",
                          "launches": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4), "event_pairs": len(prof),
                          "share_of_step": round(conv_ms / ms, 4), "tflops_fp32": round(conv_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms else 0},
         }

@@ -293,7 +293,7 @@ class GausPcgcCodec:
         if n >= 150_000:
             return 128, 48          # v6d: rows straight into the MMA fragments, 128-row tiles halve the W^T traffic per pair
         if n >= 40_000:
-            return 64, 44
+            return 64, 48
         if n >= 20_000:
             return 32, 46
         if n >= 1_500:

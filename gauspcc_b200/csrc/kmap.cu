@@ -188,13 +188,12 @@ __global__ void __launch_bounds__(KP_THREADS) kmap_pairs_fill_kernel(const i32 *
 template <int RPL>
 __global__ void __launch_bounds__(128) kmap_pairs_count_warp_kernel(const i32 *__restrict__ map, i64 n, i64 tiles, int pad,
                                                                    u32 *__restrict__ counts, u32 *__restrict__ n_real) {
-    const int lane = threadIdx.x & 31;
-    const i64 t = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (t >= tiles) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 t = blockIdx.x;                       // one CTA per tile, warp w takes offsets w, w + 4, ... ((tile, offset) cells are independent)
     const i64 r0 = t * (32 * RPL);
     u32 real = 0;
-#pragma unroll 5
-    for (int k = 0; k < GPC_K3; ++k) {
+#pragma unroll 4
+    for (int k = wid; k < GPC_K3; k += 4) {
         u32 c = 0;
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
@@ -206,20 +205,19 @@ __global__ void __launch_bounds__(128) kmap_pairs_count_warp_kernel(const i32 *_
         c = (c + pad - 1) / pad * pad;
         if (lane == 0) counts[t * (GPC_K3 + 1) + k] = c;
     }
-    if (lane == 0) { counts[t * (GPC_K3 + 1) + GPC_K3] = 0; atomicAdd(n_real, real); }
+    if (lane == 0) { if (wid == 0) counts[t * (GPC_K3 + 1) + GPC_K3] = 0; atomicAdd(n_real, real); }
 }
 
 template <int RPL>
 __global__ void __launch_bounds__(128) kmap_pairs_fill_warp_kernel(const i32 *__restrict__ map, i64 n, i64 tiles,
                                                                   const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr,
                                                                   u16 *__restrict__ pair_row, u64 *__restrict__ pairs) {
-    const int lane = threadIdx.x & 31;
-    const i64 t = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (t >= tiles) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 t = blockIdx.x;
     const i64 r0 = t * (32 * RPL);
     const u32 lt = (1u << lane) - 1u;
-#pragma unroll 5
-    for (int k = 0; k < GPC_K3; ++k) {
+#pragma unroll 4
+    for (int k = wid; k < GPC_K3; k += 4) {
         u32 p = seg[t * (GPC_K3 + 1) + k];
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
@@ -296,9 +294,9 @@ extern "C" int gpc_kmap_pairs_count(const int32_t *map, int64_t n, int tile_rows
     GPC_CUDA_CHECK(cudaMemsetAsync(n_pairs, 0, 8, st));      // n_pairs[0] = stream entries (padded), n_pairs[1] = true pairs
     if (tile_rows == 8) kmap_pairs_count_sub_kernel<8><<<cdiv(tiles, 16), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
     else if (tile_rows == 16) kmap_pairs_count_sub_kernel<16><<<cdiv(tiles, 8), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
-    else if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
-    else if (tile_rows == 64) kmap_pairs_count_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
-    else if (tile_rows == 128) kmap_pairs_count_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 32) kmap_pairs_count_warp_kernel<1><<<(unsigned)tiles, 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 64) kmap_pairs_count_warp_kernel<2><<<(unsigned)tiles, 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
+    else if (tile_rows == 128) kmap_pairs_count_warp_kernel<4><<<(unsigned)tiles, 128, 0, st>>>(map, n, tiles, pad, counts, n_pairs + 1);
     else kmap_pairs_count_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, pad, counts, n_pairs + 1);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{counts};
@@ -317,9 +315,9 @@ extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows,
     cudaStream_t st = as_stream(stream);
     if (tile_rows == 8) kmap_pairs_fill_sub_kernel<8><<<cdiv(tiles, 16), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
     else if (tile_rows == 16) kmap_pairs_fill_sub_kernel<16><<<cdiv(tiles, 8), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
-    else if (tile_rows == 32) kmap_pairs_fill_warp_kernel<1><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
-    else if (tile_rows == 64) kmap_pairs_fill_warp_kernel<2><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
-    else if (tile_rows == 128) kmap_pairs_fill_warp_kernel<4><<<cdiv(tiles, 4), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 32) kmap_pairs_fill_warp_kernel<1><<<(unsigned)tiles, 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 64) kmap_pairs_fill_warp_kernel<2><<<(unsigned)tiles, 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
+    else if (tile_rows == 128) kmap_pairs_fill_warp_kernel<4><<<(unsigned)tiles, 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
     else kmap_pairs_fill_kernel<<<(unsigned)tiles, KP_THREADS, 0, st>>>(map, n, tile_rows, seg, pair_nbr, pair_row, pairs);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
