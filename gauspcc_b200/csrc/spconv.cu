@@ -1260,7 +1260,10 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
             // tile T - 1's slot is free: its fragments were converted and its rows / offset consumed in the previous step
             if (T + 3 < ntiles)
                 issue(xa[(u + 3) & 3], xc[(u + 3) & 3], rwa[(u + 3) & 3], rwb[(u + 3) & 3], kof[(u + 3) & 3], u < 1 ? eb[h] : eb[h ^ 1], (u + 3) & 3);
-            // W of the next tile if its offset differs (warp-uniform): in flight during this tile's MMAs
+            // that was the last entry of bulk eb[h] (tile T + 3): fetch the bulk after the next one, first needed five tiles from here
+            if (u == 0) eb[h] = load_bulk(2 * kb + h + 2);
+            // W of the next tile if its offset differs (warp-uniform): in flight during this tile's MMAs.  (Requesting it as soon as
+            // the offset shows up in the 3-tile look-ahead window was measured 20 % SLOWER: the fragments then live across iterations.)
             const u32 k_next = T + 1 < ntiles ? kof[(u + 1) & 3] : k_cur;
             const bool newk = k_next != k_cur;
             uint4 n1[2][2], n2[2][2];
@@ -1301,7 +1304,6 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
 #pragma unroll
                     for (int uu = 0; uu < 2; ++uu) { w1[mt][uu] = n1[mt][uu]; w2[mt][uu] = n2[mt][uu]; }
             }
-            if (u == 3) eb[h] = load_bulk(2 * kb + h + 2);      // this bulk's last tile is done, tiles T + 1 .. T + 3 come from the other one
         }
     }
     __syncwarp();
