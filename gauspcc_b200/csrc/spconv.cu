@@ -1222,15 +1222,21 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
     u64 eb[2] = {load_bulk(0), load_bulk(1)};   // bulks 2j / 2j + 1: statically indexed (a register hand-over would wait for every load in flight)
     float4 xa[4], xc[4];
     u32 rwa[4], rwb[4], kof[4];
-    auto issue = [&](float4 &a, float4 &c, u32 &ra, u32 &rb, u32 &kk, u64 eb, int tl) {
-        const u32 nb = __shfl_sync(0xFFFFFFFFu, (u32)eb, tl * 8 + g);
-        const u32 hi = (u32)(eb >> 32);
-        ra = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t) & 0xFFFFu;               // padding entries: 0xFFFF
-        rb = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t + 1) & 0xFFFFu;
-        kk = __shfl_sync(0xFFFFFFFFu, hi, tl * 8) >> 16;                           // entry 0 of a tile is always a real pair
+    // an entry is handed out in two steps one tile apart, so that nothing waits for a shuffle: pick (shuffles into p_*), then
+    // fetch (row loads from the picked neighbour index, bookkeeping into the tile's slot)
+    u32 p_nb = 0xFFFFFFFFu, p_ra = 0xFFFFu, p_rb = 0xFFFFu, p_kk = 0;
+    auto pick = [&](u64 ebv, int tl) {
+        p_nb = __shfl_sync(0xFFFFFFFFu, (u32)ebv, tl * 8 + g);
+        const u32 hi = (u32)(ebv >> 32);
+        p_ra = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t) & 0xFFFFu;             // padding entries: 0xFFFF
+        p_rb = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t + 1) & 0xFFFFu;
+        p_kk = __shfl_sync(0xFFFFFFFFu, hi, tl * 8) >> 16;                         // entry 0 of a tile is always a real pair
+    };
+    auto fetch = [&](float4 &a, float4 &c, u32 &ra, u32 &rb, u32 &kk) {
+        ra = p_ra; rb = p_rb; kk = p_kk;
         a = make_float4(0.f, 0.f, 0.f, 0.f); c = a;
-        if (nb != 0xFFFFFFFFu) {
-            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)nb * GPC_C + 8 * t);
+        if (p_nb != 0xFFFFFFFFu) {
+            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)p_nb * GPC_C + 8 * t);
             a = __ldg(src); c = __ldg(src + 1);
         }
     };
@@ -1244,9 +1250,10 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
     uint4 w1[2][2], w2[2][2];
     u32 k_cur = 0xFFFFFFFFu;
     if (ntiles > 0) {
-        issue(xa[0], xc[0], rwa[0], rwb[0], kof[0], eb[0], 0);
-        if (ntiles > 1) issue(xa[1], xc[1], rwa[1], rwb[1], kof[1], eb[0], 1);
-        if (ntiles > 2) issue(xa[2], xc[2], rwa[2], rwb[2], kof[2], eb[0], 2);
+        pick(eb[0], 0); fetch(xa[0], xc[0], rwa[0], rwb[0], kof[0]);
+        if (ntiles > 1) { pick(eb[0], 1); fetch(xa[1], xc[1], rwa[1], rwb[1], kof[1]); }
+        if (ntiles > 2) { pick(eb[0], 2); fetch(xa[2], xc[2], rwa[2], rwb[2], kof[2]); }
+        pick(eb[0], 3);
         k_cur = kof[0];
         load_w(w1, w2, k_cur);
     }
@@ -1258,10 +1265,10 @@ __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restr
             const int T = 8 * kb + u8;
             if (T >= ntiles) break;
             // tile T - 1's slot is free: its fragments were converted and its rows / offset consumed in the previous step
-            if (T + 3 < ntiles)
-                issue(xa[(u + 3) & 3], xc[(u + 3) & 3], rwa[(u + 3) & 3], rwb[(u + 3) & 3], kof[(u + 3) & 3], u < 1 ? eb[h] : eb[h ^ 1], (u + 3) & 3);
-            // that was the last entry of bulk eb[h] (tile T + 3): fetch the bulk after the next one, first needed five tiles from here
+            if (T + 3 < ntiles) fetch(xa[(u + 3) & 3], xc[(u + 3) & 3], rwa[(u + 3) & 3], rwb[(u + 3) & 3], kof[(u + 3) & 3]);
+            // bulk eb[h] (tiles T .. T + 3) was picked completely during the previous four steps: fetch the bulk after the next one
             if (u == 0) eb[h] = load_bulk(2 * kb + h + 2);
+            pick(eb[h ^ 1], u);                          // tile T + 4
             // W of the next tile if its offset differs (warp-uniform): in flight during this tile's MMAs.  (Requesting it as soon as
             // the offset shows up in the 3-tile look-ahead window was measured 20 % SLOWER: the fragments then live across iterations.)
             const u32 k_next = T + 1 < ntiles ? kof[(u + 1) & 3] : k_cur;
