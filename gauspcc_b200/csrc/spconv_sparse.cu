@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
         const int e = k * 32 + lane;
         return e < ntiles * 8 ? __ldg(tile_base + e) : ~0ull;
     };
-    u64 eb0 = load_bulk(0), eb1 = load_bulk(1);
+    u64 eb[2] = {load_bulk(0), load_bulk(1)};            // bulks 2j / 2j + 1, statically indexed (no register hand-over of a load in flight)
     uint4 w1[2][2], w2[2][2];                            // A fragments of W^T[k] (bf16 hi / lo), [mt][u]: once per segment
     {
         const uint4 *wsrc = Wa + (size_t)sp_offset(kk) * 256 + lane;
@@ -144,26 +144,36 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
     }
     float4 xa[4], xc[4];
     u32 dsa[4], dsb[4];
-    auto issue = [&](float4 &a, float4 &c, u32 &da, u32 &db, u64 eb, int tl) {      // rows + destinations of tile `tl` of the bulk in eb
-        const u32 nb = __shfl_sync(0xFFFFFFFFu, (u32)eb, tl * 8 + g);
-        const u32 hi = (u32)(eb >> 32);
-        da = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t);
-        db = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t + 1);
+    // an entry is handed out in two steps one tile apart (as in spconv_fwd_v6d_kernel): pick = shuffles, fetch = row loads
+    u32 p_nb = 0xFFFFFFFFu, p_da = 0xFFFFFFFFu, p_db = 0xFFFFFFFFu;
+    auto pick = [&](u64 ebv, int tl) {                   // neighbour row + destinations of tile `tl` of the bulk in ebv
+        p_nb = __shfl_sync(0xFFFFFFFFu, (u32)ebv, tl * 8 + g);
+        const u32 hi = (u32)(ebv >> 32);
+        p_da = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t);
+        p_db = __shfl_sync(0xFFFFFFFFu, hi, tl * 8 + 2 * t + 1);
+    };
+    auto fetch = [&](float4 &a, float4 &c, u32 &da, u32 &db) {
+        da = p_da; db = p_db;
         a = make_float4(0.f, 0.f, 0.f, 0.f); c = a;
-        if (nb != 0xFFFFFFFFu) {
-            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)nb * GPC_C + 8 * t);
+        if (p_nb != 0xFFFFFFFFu) {
+            const float4 *src = reinterpret_cast<const float4 *>(x + (i64)p_nb * GPC_C + 8 * t);
             a = __ldg(src); c = __ldg(src + 1);
         }
     };
-    issue(xa[0], xc[0], dsa[0], dsb[0], eb0, 0);
-    if (ntiles > 1) issue(xa[1], xc[1], dsa[1], dsb[1], eb0, 1);
+    pick(eb[0], 0); fetch(xa[0], xc[0], dsa[0], dsb[0]);
+    if (ntiles > 1) { pick(eb[0], 1); fetch(xa[1], xc[1], dsa[1], dsb[1]); }
+    if (ntiles > 2) { pick(eb[0], 2); fetch(xa[2], xc[2], dsa[2], dsb[2]); }
+    pick(eb[0], 3);
 #pragma unroll 1
-    for (int k = 0; 4 * k < ntiles; ++k) {
+    for (int k = 0; 8 * k < ntiles; ++k) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int T = 4 * k + u;
+        for (int u8 = 0; u8 < 8; ++u8) {
+            const int u = u8 & 3, h = u8 >> 2;
+            const int T = 8 * k + u8;
             if (T >= ntiles) break;
-            if (T + 2 < ntiles) issue(xa[(u + 2) & 3], xc[(u + 2) & 3], dsa[(u + 2) & 3], dsb[(u + 2) & 3], u < 2 ? eb0 : eb1, (u + 2) & 3);
+            if (T + 3 < ntiles) fetch(xa[(u + 3) & 3], xc[(u + 3) & 3], dsa[(u + 3) & 3], dsb[(u + 3) & 3]);
+            if (u == 0) eb[h] = load_bulk(2 * k + h + 2);        // bulk eb[h] was picked completely during the previous four steps
+            pick(eb[h ^ 1], u);                                  // tile T + 4
             u32 xf1[2][2], xf2[2][2];
             split_bf16(xa[u].x, xa[u].y, xf1[0][0], xf2[0][0]);
             split_bf16(xa[u].z, xa[u].w, xf1[0][1], xf2[0][1]);
@@ -185,8 +195,6 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
             if (dsa[u] != 0xFFFFFFFFu) reinterpret_cast<float4 *>(contrib)[(size_t)dsa[u] * 8 + g] = make_float4(d[0][0], d[0][2], d[1][0], d[1][2]);
             if (dsb[u] != 0xFFFFFFFFu) reinterpret_cast<float4 *>(contrib)[(size_t)dsb[u] * 8 + g] = make_float4(d[0][1], d[0][3], d[1][1], d[1][3]);
         }
-        eb0 = eb1;
-        eb1 = load_bulk(k + 2);
     }
 }
 
