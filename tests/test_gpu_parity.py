@@ -250,6 +250,61 @@ def test_codec_sparse_conv_vs_oracle(env_sparse, n, seed, ext):
 
 
 @pytest.fixture(scope="module")
+def env_v6d(env):
+    """A codec whose levels ALL run the v6d conv (rows straight into the MMA fragments) with 128-row tiles: what the levels
+    with >= 150 K rows of a full-size scene take."""
+    from gauspcc_b200.codec import GausPcgcCodec
+    codec = GausPcgcCodec(env["codec"].w, env["dev"], tile_rows=128)
+    codec.conv_variant = 48
+    codec6 = GausPcgcCodec(env["codec"].w, env["dev"], tile_rows=64)       # v6, one warp per 64-row tile, on every level
+    codec6.conv_variant = 42
+    return dict(env, codec=codec, codec6=codec6)
+
+
+@pytest.mark.parametrize("n,ext,tile", [(30000, 16, 128), (30000, 16, 64), (30000, 16, 32), (2000, 6, 128), (700, 4, 128),
+                                        (129, 4, 128), (5, 2, 128)])
+def test_sparse_conv_v6d(env_v6d, n, ext, tile):
+    """v6d against the fp32 oracle conv and, bit for bit, against v6 (same products, same summation order per row); ragged last
+    tile, fewer than four 8-pair tiles per warp, entry bulks that end inside the unrolled 8-tile body"""
+    from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
+    from oracle import oracle as O
+    codec, w = env_v6d["codec"], env_v6d["w"]
+    codec.tile_rows = tile
+    try:
+        xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
+        xyz = xyz[O.sort_zyx_perm(xyz)]
+        keys, _ = _keys_of(codec, xyz)
+        km = codec.build_kmap(keys)
+        assert km.tile_rows == tile and not km.sparse
+        ref_km = O.kmap(xyz, 5)
+        assert km.n_real == int((ref_km >= 0).sum())
+        rng = np.random.default_rng(0)
+        x = rng.normal(size=(n, 32)).astype(np.float32)
+        res = rng.normal(size=(n, 32)).astype(np.float32)
+        xd, rd = torch.tensor(x, device=codec.dev), torch.tensor(res, device=codec.dev)
+        ref = O.conv(x, w["target_resnet.2.conv1.kernel"], ref_km)
+        scale = max(np.abs(ref).max(), 1.0)
+        y = codec.conv(xd, 7, km).cpu().numpy()
+        assert np.abs(y - ref).max() <= 2e-5 * scale
+        y2 = codec.conv(xd, 7, km, residual=rd, relu=True).cpu().numpy()
+        assert np.abs(y2 - np.maximum(ref + res, 0)).max() <= 2e-5 * scale
+        assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)            # deterministic
+        base = env_v6d["codec6"]
+        base.sparse_max_density = 0
+        km6 = base.build_kmap(keys)
+        assert km6.v6_variant == 42 and km6.tile_rows == 64
+        assert np.array_equal(base.conv(xd, 7, km6).cpu().numpy(), y)            # v6: same sums bit for bit
+    finally:
+        codec.tile_rows = 128
+
+
+@pytest.mark.parametrize("n,seed,ext", [(20000, 1, 16), (2500, 5, 12)])
+def test_codec_v6d_vs_oracle(env_v6d, n, seed, ext):
+    """the whole codec with every level on v6d<128>: same bars as test_codec_vs_oracle"""
+    test_codec_vs_oracle(env_v6d, n, seed, ext)
+
+
+@pytest.fixture(scope="module")
 def env_umma(env):
     """A second codec whose levels ALL run the tcgen05 conv (split rows), whatever their size and density."""
     from gauspcc_b200.codec import GausPcgcCodec
