@@ -126,6 +126,7 @@ class GausPcgcCodec:
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
+        self._pinned_dec: Optional[torch.Tensor] = None
         self._launch_base = 0
         self.last_stats: Dict[str, float] = {}
         self._segments: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
@@ -663,14 +664,14 @@ class GausPcgcCodec:
         ws = self._ws(ws_b)
         self._call("gpc_sort_pairs", _ptr(keys), _ptr(None), _ptr(skeys), _ptr(perm), n0, xf, _ptr(ws), ws_b, self._stream())
         cur = Level(skeys, bo[perm.long()] if n0 else bo, n0)
-        pin = None
+        pin = self._pinned_dec                     # staging for CDF rows / symbols, kept across calls (grown geometrically)
         t_wait = t_ac = 0.0
         for g in range(0, len(streams), 4):
             n_child = self._popcount(cur.occ) if forced_occ is None else int(forced_occ[g // 4].shape[0])
             child, u = self.level_features(cur, n_child)
             occ = torch.zeros(n_child, dtype=torch.uint8, device=self.dev)
-            if pin is None or pin.numel() < n_child * 40:
-                pin = torch.empty(n_child * 40 + 64, dtype=torch.uint8, pin_memory=True)
+            if forced_occ is None and (pin is None or pin.numel() < n_child * 40):
+                pin = self._pinned_dec = torch.empty(int(n_child * 40 * 1.5) + 4096, dtype=torch.uint8, pin_memory=True)
             for i in range(4):
                 A = W.STAGE_ALPHABETS[i]
                 cdf_d = self._empty((n_child, A + 1), torch.int16)
