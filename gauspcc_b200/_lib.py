@@ -82,6 +82,9 @@ SIGNATURES = {
     "gpc_merge_symbol": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "gpc_ac_encode_h": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, C.POINTER(c_i64)]),
     "gpc_ac_decode_h": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp]),
+    "gpc_ac_decode_state_bytes": (c_i64, []),
+    "gpc_ac_decode_begin_h": (c_int, [c_vp, c_vp, c_i64]),
+    "gpc_ac_decode_more_h": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
     "gpc_ac_encode_lohi_h": (c_int, [c_vp, c_i64, c_vp, c_i64, C.POINTER(c_i64)]),
 }
 

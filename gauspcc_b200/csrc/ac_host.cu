@@ -195,14 +195,25 @@ __attribute__((target("avx2"))) static inline int sym16_avx2(const u16 *row, u64
 #define GPC_AC_FAST_TARGET
 #endif
 
+// Decoder state between calls: one stream may be decoded in several pieces (gpc_ac_decode_begin_h / _more_h), e.g. while
+// later CDF rows are still being computed.
+struct AcDecState {
+    BitReservoir br;
+    u32 low, high, value;
+};
+static inline void ac_decode_start(AcDecState &st, const u8 *in, i64 in_len) {
+    st.br = BitReservoir{in, in_len, 0, 0, 0};
+    st.br.refill();
+    st.low = 0; st.high = 0xFFFFFFFFu; st.value = st.br.take(32);
+    st.br.refill();
+}
+
 template <int LP /* 3, 5, 17 or 0 = any */, bool FAST>
-static inline __attribute__((always_inline)) void ac_decode_body(const u16 *cdf, const u8 *in, i64 in_len, i64 n, int Lp_rt, u8 *sym) {
+static inline __attribute__((always_inline)) void ac_decode_body(AcDecState &state, const u16 *cdf, i64 n, int Lp_rt, u8 *sym) {
     constexpr bool BINARY = LP == 3;
     const int Lp = LP ? LP : Lp_rt;
-    BitReservoir br{in, in_len, 0, 0, 0};
-    br.refill();
-    u32 low = 0, high = 0xFFFFFFFFu, value = br.take(32);
-    br.refill();
+    BitReservoir br = state.br;                                                 // locals: kept in registers across the loop
+    u32 low = state.low, high = state.high, value = state.value;
     const int top_sym = Lp - 2;
     auto clz32 = [](u32 x) -> int {
 #if defined(__x86_64__)
@@ -261,26 +272,48 @@ static inline __attribute__((always_inline)) void ac_decode_body(const u16 *cdf,
             value = ((value << u) ^ (u ? 0x80000000u : 0u)) | br.take(u);
         }
     }
+    state.br = br;
+    state.low = low; state.high = high; state.value = value;
 }
-GPC_AC_FAST_TARGET static void ac_decode_fast(const u16 *cdf, const u8 *in, i64 in_len, i64 n, int Lp, u8 *sym) {
-    if (Lp == 3) ac_decode_body<3, true>(cdf, in, in_len, n, Lp, sym);
-    else if (Lp == 5) ac_decode_body<5, true>(cdf, in, in_len, n, Lp, sym);
-    else if (Lp == 17) ac_decode_body<17, true>(cdf, in, in_len, n, Lp, sym);
-    else ac_decode_body<0, true>(cdf, in, in_len, n, Lp, sym);
+GPC_AC_FAST_TARGET static void ac_decode_fast(AcDecState &st, const u16 *cdf, i64 n, int Lp, u8 *sym) {
+    if (Lp == 3) ac_decode_body<3, true>(st, cdf, n, Lp, sym);
+    else if (Lp == 5) ac_decode_body<5, true>(st, cdf, n, Lp, sym);
+    else if (Lp == 17) ac_decode_body<17, true>(st, cdf, n, Lp, sym);
+    else ac_decode_body<0, true>(st, cdf, n, Lp, sym);
 }
-static void ac_decode_base(const u16 *cdf, const u8 *in, i64 in_len, i64 n, int Lp, u8 *sym) {
-    if (Lp == 3) ac_decode_body<3, false>(cdf, in, in_len, n, Lp, sym);
-    else if (Lp == 5) ac_decode_body<5, false>(cdf, in, in_len, n, Lp, sym);
-    else ac_decode_body<0, false>(cdf, in, in_len, n, Lp, sym);
+static void ac_decode_base(AcDecState &st, const u16 *cdf, i64 n, int Lp, u8 *sym) {
+    if (Lp == 3) ac_decode_body<3, false>(st, cdf, n, Lp, sym);
+    else if (Lp == 5) ac_decode_body<5, false>(st, cdf, n, Lp, sym);
+    else ac_decode_body<0, false>(st, cdf, n, Lp, sym);
+}
+static void ac_decode_dispatch(AcDecState &st, const u16 *cdf, i64 n, int Lp, u8 *sym) {
+#if defined(__x86_64__)
+    static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+    if (fast) { ac_decode_fast(st, cdf, n, Lp, sym); return; }
+#endif
+    ac_decode_base(st, cdf, n, Lp, sym);
 }
 
 extern "C" int gpc_ac_decode_h(const uint16_t *cdf, const uint8_t *in, int64_t in_len, int64_t n, int Lp, uint8_t *sym) {
     GPC_REQUIRE(Lp >= 3 && Lp <= 17 && sym, GPC_EINVAL, "bad argument");
-#if defined(__x86_64__)
-    static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
-    if (fast) { ac_decode_fast(cdf, in, in_len, n, Lp, sym); return GPC_OK; }
-#endif
-    ac_decode_base(cdf, in, in_len, n, Lp, sym);
+    AcDecState st;
+    ac_decode_start(st, in, in_len);
+    ac_decode_dispatch(st, cdf, n, Lp, sym);
+    return GPC_OK;
+}
+
+// The same decoder in pieces: `state` is caller-owned memory of gpc_ac_decode_state_bytes() bytes; begin binds it to a stream
+// (which must stay alive), every `more` call decodes the next n symbols with the next n CDF rows.  Any split of the rows gives the
+// symbols gpc_ac_decode_h gives (tests/test_cabi_cpu.py).
+extern "C" int64_t gpc_ac_decode_state_bytes(void) { return (int64_t)sizeof(AcDecState); }
+extern "C" int gpc_ac_decode_begin_h(void *state, const uint8_t *in, int64_t in_len) {
+    GPC_REQUIRE(state && (in || in_len == 0) && in_len >= 0, GPC_EINVAL, "bad argument");
+    ac_decode_start(*(AcDecState *)state, in, in_len);
+    return GPC_OK;
+}
+extern "C" int gpc_ac_decode_more_h(void *state, const uint16_t *cdf, int64_t n, int Lp, uint8_t *sym) {
+    GPC_REQUIRE(state && Lp >= 3 && Lp <= 17 && (n == 0 || (cdf && sym)) && n >= 0, GPC_EINVAL, "bad argument");
+    ac_decode_dispatch(*(AcDecState *)state, cdf, n, Lp, sym);
     return GPC_OK;
 }
 

@@ -243,6 +243,13 @@ int gpc_ac_encode_h(const uint16_t *cdf_h, const uint8_t *sym_h, int64_t n, int 
                     uint8_t *out_h, int64_t cap, int64_t *out_len_h);
 int gpc_ac_decode_h(const uint16_t *cdf_h, const uint8_t *in_h, int64_t in_len, int64_t n, int Lp,
                     uint8_t *sym_h);
+/* gpc_ac_decode_h in pieces (one stream decoded chunk by chunk while later CDF rows are still being computed; the four stage
+ * streams of a level then decode concurrently, pcc_utils.py:319-366 run as a wavefront).  `state_h`: caller-owned, state_bytes()
+ * bytes; begin binds it to a stream that must outlive it; each `more` decodes the next n symbols from the next n CDF rows.
+ * Any split yields the symbols of the one-shot call. */
+int64_t gpc_ac_decode_state_bytes(void);
+int gpc_ac_decode_begin_h(void *state_h, const uint8_t *in_h, int64_t in_len);
+int gpc_ac_decode_more_h(void *state_h, const uint16_t *cdf_h, int64_t n, int Lp, uint8_t *sym_h);
 /* same bitstream as gpc_ac_encode_h, fed with the (c_low, c_high) words of gpc_head_cdf_sym */
 int gpc_ac_encode_lohi_h(const uint32_t *lohi_h, int64_t n, uint8_t *out_h, int64_t cap, int64_t *out_len_h);
 

@@ -101,6 +101,32 @@ def test_host_range_decoder_underflow_heavy(A):
     assert np.array_equal(O.ac_decode(cdf, stream).astype(np.uint8), sym)
 
 
+@pytest.mark.parametrize("A", [2, 4, 16])
+def test_host_range_decoder_in_pieces(A):
+    """gpc_ac_decode_begin_h / _more_h: any split of the rows decodes to the symbols of the one-shot call (empty pieces, single
+    symbols, a piece boundary right after the stream's last byte)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5 + A)
+    n = 20000
+    p = rng.dirichlet(np.ones(A) * 0.5, size=n)
+    c = np.clip(np.cumsum(p, axis=1), 0, 1)
+    cdf = np.zeros((n, A + 1), dtype=np.uint16)
+    cdf[:, 1:] = (np.rint(c * (65536 - A)).astype(np.int64) + np.arange(1, A + 1)).astype(np.uint16)
+    sym = (rng.random(n)[:, None] > c).sum(1).clip(0, A - 1).astype(np.uint8)
+    stream = _enc(lib, cdf, sym)
+    assert np.array_equal(_dec(lib, cdf, stream), sym)
+    buf = (C.c_char * max(len(stream), 1)).from_buffer_copy(stream)
+    for cuts in ([0, n], [0, 0, 1, 2, 7, 7, 4096, 4097, n - 1, n], sorted(rng.integers(0, n + 1, size=40).tolist() + [0, n])):
+        state = (C.c_char * int(lib.gpc_ac_decode_state_bytes()))()
+        assert lib.gpc_ac_decode_begin_h(C.cast(state, C.c_void_p), C.cast(buf, C.c_void_p), len(stream)) == 0
+        out = np.full(n, 255, np.uint8)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            rows, dst = cdf[a:b], out[a:b]
+            assert lib.gpc_ac_decode_more_h(C.cast(state, C.c_void_p), rows.ctypes.data_as(C.c_void_p), b - a, A + 1,
+                                            dst.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(out, sym)
+
+
 def test_host_range_coder_rejects_bad_symbol():
     lib = _lib.load()
     cdf = np.array([[0, 100, 0]], dtype=np.uint16)
