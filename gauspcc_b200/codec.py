@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import queue
 import time
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
@@ -127,6 +128,11 @@ class GausPcgcCodec:
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_thr))
         self._pinned: Optional[torch.Tensor] = None
         self._pinned_dec: Optional[torch.Tensor] = None
+        # decoder wavefront (stages of a level overlap chunk by chunk): levels with >= wave_min_rows rows, chunks of wave_chunk_rows
+        # rows (a multiple of 8192 = the sparse conv's row blocks and of the v6d tile heights)
+        self.wave_decode = os.environ.get("GPC_WAVE_DECODE", "1") != "0"
+        self.wave_min_rows = int(os.environ.get("GPC_WAVE_MIN_ROWS", 150_000))
+        self.wave_chunk_rows = int(os.environ.get("GPC_WAVE_CHUNK_ROWS", 32768))
         self._launch_base = 0
         self.last_stats: Dict[str, float] = {}
         self._segments: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
@@ -387,10 +393,21 @@ class GausPcgcCodec:
         return xs
 
     def conv(self, x: torch.Tensor, widx: int, km: KMap, residual: Optional[torch.Tensor] = None, relu: bool = False,
-             out: Optional[torch.Tensor] = None, fmt: str = "f32"):
+             out: Optional[torch.Tensor] = None, fmt: str = "f32", rows: Optional[Tuple[int, int]] = None):
         """One sparse conv.  Activations are fp32 rows (float32 tensors) or split rows (int32 tensors, tcgen05 levels
-        only); fmt = "f32" | "split" | "both" selects what is written ("both" returns (f32, split))."""
+        only); fmt = "f32" | "split" | "both" selects what is written ("both" returns (f32, split)).
+        rows = (r0, r1): only the output rows [r0, r1) of `out` are computed (decoder wavefront; v6d and sparse levels)."""
         n = x.shape[0]
+        if rows is not None:
+            assert out is not None and fmt == "f32" and x.dtype == torch.float32 and not km.cta_rows
+            if km.sparse:
+                self._call("gpc_spconv_sparse_fwd_rows", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs),
+                           _ptr(km.rowptr), n, km.n_pairs, _ptr(km.contrib), _ptr(residual), 1 if relu else 0, _ptr(out),
+                           rows[0], rows[1], self._stream())
+            else:
+                self._call("gpc_spconv_fwd_v6_rows", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n,
+                           km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(out), km.v6_variant, rows[0], rows[1], self._stream())
+            return out
         if km.cta_rows:
             xs = x if x.dtype == torch.int32 else self.split_rows(x)
             y = (out if out is not None else self._empty((n, 32), torch.float32)) if fmt in ("f32", "both") else None
@@ -633,6 +650,136 @@ class GausPcgcCodec:
         return base_xyz_h, base_occ_h, streams, aux
 
     # ------------------------------------------------------------------ decode
+    # ------------------------------------------------------------------ decoder: the four stages of a level as a wavefront
+    # pcc_utils.py:319-366 decodes a level stage by stage: CDFs of stage i for ALL rows -> range decoder (one serial stream) -> symbols
+    # -> stage i+1.  The dependency is local, though: stage i+1 of a row needs the stage-i symbols of the rows within two 5^3 convs
+    # of it, and rows are sorted by (z, y, x).  So the level is cut into chunks of rows; as soon as stage i is decoded for chunks
+    # <= c + 2 the GPU computes the stage-(i+1) CDFs of chunk c, and the four stage streams decode on four host threads, each a few
+    # chunks behind the previous one.  Same kernels, same sums, same bitstream; the serial range decoder (0.28 s of a 0.35 s decode
+    # at 1M anchors) overlaps with itself.
+    def _wave_ok(self, child: Level, n: int) -> bool:
+        km = child.kmap
+        if not self.wave_decode or n < self.wave_min_rows or km.cta_rows:
+            return False
+        if not (km.sparse or (getattr(km, "v6_variant", 0) == 48 and self.wave_chunk_rows % km.tile_rows == 0)):
+            return False
+        ch = self.wave_chunk_rows
+        nc = (n + ch - 1) // ch
+        if nc < 3:
+            return False
+        # every 5^3 neighbour of a row of chunk c must lie in chunks c-1 .. c+1: first z of chunk c minus last z of chunk c-2 >= 3
+        first = torch.arange(0, nc, device=self.dev) * ch
+        last = torch.clamp(first + ch, max=n) - 1
+        z = (child.keys[torch.cat([first, last])] >> 42).cpu().numpy()
+        zf, zl = z[:nc], z[nc:]
+        return bool(np.all(zf[2:] - zl[:-2] >= 3))
+
+    def _decode_level_wavefront(self, u, child: Level, n: int, streams: List[bytes], occ: torch.Tensor):
+        km, ch = child.kmap, self.wave_chunk_rows
+        nc = (n + ch - 1) // ch
+        chunks = [(c * ch, min((c + 1) * ch, n)) for c in range(nc)]
+        u = u[0] if isinstance(u, tuple) else u
+        Lps = [a + 1 for a in W.STAGE_ALPHABETS]
+        # pinned staging: the four stages' CDF rows and symbols live at the same time
+        need = n * (2 * sum(Lps) + 4) + 4096
+        if self._pinned_dec is None or self._pinned_dec.numel() < need:
+            self._pinned_dec = torch.empty(int(need * 1.5), dtype=torch.uint8, pin_memory=True)
+        pin, off = self._pinned_dec, 0
+        cdf_h, sym_h = [], []
+        for Lp in Lps:
+            cdf_h.append(pin[off:off + n * Lp * 2].view(torch.int16).view(n, Lp))
+            off += (n * Lp * 2 + 63) // 64 * 64
+        for _ in range(4):
+            sym_h.append(pin[off:off + n])
+            off += (n + 63) // 64 * 64
+        cdf_d = [self._empty((n, Lp), torch.int16) for Lp in Lps]
+        sym_d = [self._empty((n,), torch.uint8) for _ in range(4)]
+        f = [None] + [self._empty((n, 32), torch.float32) for _ in range(3)]
+        t0 = [self._empty((n, 32), torch.float32) for _ in range(4)]
+        t1 = [self._empty((n, 32), torch.float32) for _ in range(4)]
+        stream = torch.cuda.current_stream(self.dev)
+        ev_q = [queue.Queue() for _ in range(4)]
+        done_q: "queue.Queue" = queue.Queue()
+        ac_s = [0.0] * 4
+        state_bytes = int(self.lib.gpc_ac_decode_state_bytes())
+
+        def worker(i: int):
+            try:
+                st = C.create_string_buffer(state_bytes)
+                data = streams[i]
+                buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data if len(data) else b"\0")
+                _lib.check(self.lib.gpc_ac_decode_begin_h(C.cast(st, C.c_void_p), C.cast(buf, C.c_void_p), len(data)), "gpc_ac_decode_begin_h")
+                cdf_np, sym_np = cdf_h[i].numpy().view(np.uint16), sym_h[i].numpy()
+                for c, (r0, r1) in enumerate(chunks):
+                    ev = ev_q[i].get()
+                    if ev is None:
+                        return
+                    ev.synchronize()
+                    tb = time.perf_counter()
+                    _lib.check(self.lib.gpc_ac_decode_more_h(C.cast(st, C.c_void_p), cdf_np[r0:r1].ctypes.data_as(C.c_void_p), r1 - r0,
+                                                             Lps[i], sym_np[r0:r1].ctypes.data_as(C.c_void_p)), "gpc_ac_decode_more_h")
+                    ac_s[i] += time.perf_counter() - tb
+                    done_q.put((i, c, None))
+            except BaseException as e:          # noqa: BLE001 -- handed to the main thread, which re-raises
+                done_q.put((i, -1, e))
+
+        def emit_cdf(i: int, c: int):
+            """head of stage i on chunk c -> D2H -> event for decoder thread i"""
+            r0, r1 = chunks[c]
+            w1, b1, w2, b2 = self.w.head[i]
+            self._call("gpc_head_cdf", _ptr(t1[i][r0:r1]), r1 - r0, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i],
+                       _ptr(cdf_d[i][r0:r1]), _ptr(None), self._stream())
+            cdf_h[i][r0:r1].copy_(cdf_d[i][r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            ev_q[i].put(ev)
+
+        workers = [self.pool.submit(worker, i) for i in range(4)]
+        t_wait = 0.0
+        try:
+            # stage 0 needs no symbols: whole level at once, CDFs handed over chunk by chunk
+            c0, c1 = W.stage_convs(0)
+            self.conv(u, c0, km, relu=True, out=t0[0])
+            self.conv(t0[0], c1, km, out=t1[0])
+            for c in range(nc):
+                emit_cdf(0, c)
+            pending = 4 * nc
+            while pending:
+                tb = time.perf_counter()
+                i, c, err = done_q.get()
+                t_wait += time.perf_counter() - tb
+                if err is not None:
+                    raise err
+                pending -= 1
+                r0, r1 = chunks[c]
+                sym_d[i][r0:r1].copy_(sym_h[i][r0:r1], non_blocking=True)
+                self._call("gpc_merge_symbol", _ptr(occ[r0:r1]), r1 - r0, STAGE_SHIFT[i], _ptr(sym_d[i][r0:r1]), self._stream())
+                if i == 3:
+                    continue
+                j = i + 1
+                k0, k1 = W.stage_convs(j)
+                self._call("gpc_add_ctx_embed", _ptr(u[r0:r1]), _ptr(occ[r0:r1]), CTX_SHIFT[j], _ptr(self.w.stage_emb[j]), r1 - r0,
+                           _ptr(f[j][r0:r1]), self._stream())
+                last = c == nc - 1
+                for cc in ([c - 1] if c >= 1 else []) + ([c] if last else []):          # first conv: inputs of chunks cc-1 .. cc+1 are there
+                    self.conv(f[j], k0, km, relu=True, out=t0[j], rows=chunks[cc])
+                for cc in ([c - 2] if c >= 2 else []) + ([c - 1, c] if last else []):
+                    if cc < 0:
+                        continue
+                    self.conv(t0[j], k1, km, out=t1[j], rows=chunks[cc])
+                    emit_cdf(j, cc)
+        except BaseException:
+            for q in ev_q:
+                q.put(None)                       # let the decoder threads go
+            raise
+        finally:
+            for w_ in workers:
+                try:
+                    w_.result()
+                except BaseException:             # noqa: BLE001 -- the first error is already on its way up
+                    pass
+        return t_wait, max(ac_s)
+
     def decode(self, base_xyz: np.ndarray, base_occ: np.ndarray, streams: List[bytes], scale: float = 1.0,
                forced_occ: Optional[List[torch.Tensor]] = None, sorted_rows: bool = False) -> torch.Tensor:
         """-> float32 [N,3] CUDA, rows in the reference's order (children of (z,y,x)-sorted parents, octant ascending), or,
@@ -672,6 +819,13 @@ class GausPcgcCodec:
             occ = torch.zeros(n_child, dtype=torch.uint8, device=self.dev)
             if forced_occ is None and (pin is None or pin.numel() < n_child * 40):
                 pin = self._pinned_dec = torch.empty(int(n_child * 40 * 1.5) + 4096, dtype=torch.uint8, pin_memory=True)
+            if forced_occ is None and self._wave_ok(child, n_child):
+                dw, da = self._decode_level_wavefront(u, child, n_child, streams[g:g + 4], occ)
+                t_wait += dw
+                t_ac += da
+                child.occ = occ
+                cur = child
+                continue
             for i in range(4):
                 A = W.STAGE_ALPHABETS[i]
                 cdf_d = self._empty((n_child, A + 1), torch.int16)

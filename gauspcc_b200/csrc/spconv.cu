@@ -1203,11 +1203,12 @@ __global__ void __launch_bounds__(32 * G) spconv_fwd_v6_kernel(const float *__re
 template <int TW>
 __global__ void __launch_bounds__(32) spconv_fwd_v6d_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
                                                             const u32 *__restrict__ seg_g, const u64 *__restrict__ pairs, i64 n,
-                                                            const float *__restrict__ residual, int flags, float *__restrict__ y) {
+                                                            const float *__restrict__ residual, int flags, float *__restrict__ y,
+                                                            i64 tile0) {
     __shared__ float acc[TW][SC6_ACC];
     const int lane = threadIdx.x;
     const int g = lane >> 2, t = lane & 3;
-    const i64 st = blockIdx.x;
+    const i64 st = tile0 + blockIdx.x;                   // tiles [tile0, tile0 + gridDim.x) of the level
     const i64 r0 = st * TW;
     const int rows = (int)min((i64)TW, n - r0);
     const u32 p_begin = __ldg(seg_g + st * (GPC_K3 + 1));
@@ -1371,9 +1372,9 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
         if (tile_rows == 32) return launch_spconv_v6<32, 4, 8>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 48) {          // v6d: rows straight into the MMA fragments (no shared-memory gather ring)
         const i64 tiles = (n + tile_rows - 1) / tile_rows;
-        if (tile_rows == 64) { spconv_fwd_v6d_kernel<64><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
-        if (tile_rows == 32) { spconv_fwd_v6d_kernel<32><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
-        if (tile_rows == 128) { spconv_fwd_v6d_kernel<128><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y); GPC_LAUNCH_CHECK(); return GPC_OK; }
+        if (tile_rows == 64) { spconv_fwd_v6d_kernel<64><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y, 0); GPC_LAUNCH_CHECK(); return GPC_OK; }
+        if (tile_rows == 32) { spconv_fwd_v6d_kernel<32><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y, 0); GPC_LAUNCH_CHECK(); return GPC_OK; }
+        if (tile_rows == 128) { spconv_fwd_v6d_kernel<128><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y, 0); GPC_LAUNCH_CHECK(); return GPC_OK; }
     } else if (variant == 47) {          // split offsets over 16 warps
         if (tile_rows == 8) return launch_spconv_v6<8, 4, 16>(x, Wa, seg, pairs, n, residual, flags, y, st);
     } else if (variant == 45) {          // split offsets over 2 warps
@@ -1383,6 +1384,25 @@ extern "C" int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t 
     }
     gpc_set_error("unsupported conv v6 variant %d / tile_rows %d", variant, tile_rows);
     return GPC_EINVAL;
+}
+
+// v6d (variant 48) for the output rows [row0, row1) only: row0 a multiple of tile_rows, row1 a multiple of tile_rows or n.  x, y,
+// residual and the pair stream are the level's.  Used by the decoder's stage wavefront (codec.py).
+extern "C" int gpc_spconv_fwd_v6_rows(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs, int64_t n,
+                                      int tile_rows, const float *residual, int flags, float *y, int variant, int64_t row0,
+                                      int64_t row1, void *stream) {
+    if (n <= 0 || row1 <= row0) return GPC_OK;
+    GPC_REQUIRE(x != y, GPC_EINVAL, "conv is out of place (rows are gathered from x while y is written)");
+    GPC_REQUIRE(variant == 48 && (tile_rows == 128 || tile_rows == 64 || tile_rows == 32), GPC_EINVAL, "row ranges: v6d (variant 48) only");
+    GPC_REQUIRE(row0 >= 0 && row1 <= n && row0 % tile_rows == 0 && (row1 % tile_rows == 0 || row1 == n), GPC_EINVAL,
+                "row range must be made of whole tiles");
+    cudaStream_t st = as_stream(stream);
+    const i64 tile0 = row0 / tile_rows, tiles = (row1 - row0 + tile_rows - 1) / tile_rows;
+    if (tile_rows == 128) spconv_fwd_v6d_kernel<128><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y, tile0);
+    else if (tile_rows == 64) spconv_fwd_v6d_kernel<64><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y, tile0);
+    else spconv_fwd_v6d_kernel<32><<<(unsigned)tiles, 32, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n, residual, flags, y, tile0);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
 }
 
 

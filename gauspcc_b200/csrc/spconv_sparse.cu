@@ -109,14 +109,14 @@ __global__ void __launch_bounds__(128) sp_fill_kernel(const i32 *__restrict__ ma
 // (2 x LDG.128 per lane).  Entries are fetched 32 at a time (4 tiles, one coalesced 256 B load) and handed out by shuffles; the rows
 // of tile T + 2 are requested before tile T is multiplied (four register slots, indexed statically by the unrolled loop).
 __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
-                                                           const u32 *__restrict__ seg, const u64 *__restrict__ pairs, i64 n_seg,
+                                                           const u32 *__restrict__ seg, const u64 *__restrict__ pairs, i64 seg0, i64 n_seg,
                                                            int SP_SPLIT, float *__restrict__ contrib) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     // SP_SPLIT warps per segment (chosen by the host from the average segment length): the segments of the offsets next to the
     // centre are 10-50 x longer than the rest; a long one (>= 8 tiles per part) is cut into up to SP_SPLIT tile ranges so that the
     // tail of the launch is not a few warps deep.  Levels with short segments launch one warp per segment.
     const i64 wg = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
-    const i64 i = wg / SP_SPLIT;
+    const i64 i = seg0 + wg / SP_SPLIT;                  // segments [seg0, n_seg) of this launch (a row range = a range of 8192-row blocks)
     const int part = (int)(wg % SP_SPLIT);
     if (i >= n_seg) return;
     const i64 b = i / SP_KK;
@@ -203,12 +203,12 @@ constexpr int SP_ROWS = 64;        // rows per warp
 constexpr int SP_ACC = 36;
 
 __global__ void __launch_bounds__(128) sp_centre_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
-                                                        const u32 *__restrict__ rowptr, const float *__restrict__ contrib, i64 n,
+                                                        const u32 *__restrict__ rowptr, const float *__restrict__ contrib, i64 row0, i64 n,
                                                         const float *__restrict__ residual, int flags, float *__restrict__ y) {
     __shared__ float acc_all[4][SP_ROWS][SP_ACC];
     float (*acc)[SP_ACC] = acc_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const i64 r0 = ((i64)blockIdx.x * 4 + (threadIdx.x >> 5)) * SP_ROWS;
+    const i64 r0 = row0 + ((i64)blockIdx.x * 4 + (threadIdx.x >> 5)) * SP_ROWS;       // rows [row0, n) of this launch
     if (r0 >= n) return;
     uint4 w1[2][2], w2[2][2];
     {
@@ -366,19 +366,34 @@ extern "C" int gpc_kmap_sparse_fill(const int32_t *map, int64_t n, const uint32_
 
 // y[o,:] = act( W[centre]^T x[o,:] + sum over the row's stragglers, ascending offset (+ residual[o,:]) ).  Wa = this conv's slice of
 // gpc_spconv_pack_weights_frag; contrib = caller scratch of max(stragglers, 1) * 32 floats (fully rewritten by every call).
+static int sp_fwd_rows(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs, const uint32_t *rowptr, int64_t n,
+                       int64_t n_entries, float *contrib, const float *residual, int flags, float *y, int64_t row0, int64_t row1,
+                       void *stream) {
+    if (n <= 0 || row1 <= row0) return GPC_OK;
+    GPC_REQUIRE(x != y, GPC_EINVAL, "conv is out of place (rows are gathered from x while y is written)");
+    GPC_REQUIRE(row0 >= 0 && row1 <= n && row0 % SP_TB == 0 && (row1 % SP_TB == 0 || row1 == n), GPC_EINVAL,
+                "row range must be made of whole 8192-row blocks");
+    cudaStream_t st = as_stream(stream);
+    const i64 nb = (n + SP_TB - 1) / SP_TB, n_seg = nb * SP_KK;
+    const i64 seg0 = row0 / SP_TB * SP_KK, seg1 = (row1 + SP_TB - 1) / SP_TB * SP_KK;
+    if (n_entries > 0) {
+        const int split = n_entries >= 256 * n_seg ? 8 : (n_entries >= 64 * n_seg ? 4 : 1);      // by the level, not by the range
+        sp_straggler_kernel<<<cdiv((seg1 - seg0) * split, 4), 128, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, seg0, seg1, split, contrib);
+        GPC_LAUNCH_CHECK();
+    }
+    sp_centre_kernel<<<cdiv(row1 - row0, 4 * SP_ROWS), 128, 0, st>>>(x, (const uint4 *)Wa, rowptr, contrib, row0, row1, residual, flags, y);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
 extern "C" int gpc_spconv_sparse_fwd(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
                                      const uint32_t *rowptr, int64_t n, int64_t n_entries, float *contrib, const float *residual,
                                      int flags, float *y, void *stream) {
-    if (n <= 0) return GPC_OK;
-    GPC_REQUIRE(x != y, GPC_EINVAL, "conv is out of place (rows are gathered from x while y is written)");
-    cudaStream_t st = as_stream(stream);
-    const i64 nb = (n + SP_TB - 1) / SP_TB, n_seg = nb * SP_KK;
-    if (n_entries > 0) {
-        const int split = n_entries >= 256 * n_seg ? 8 : (n_entries >= 64 * n_seg ? 4 : 1);
-        sp_straggler_kernel<<<cdiv(n_seg * split, 4), 128, 0, st>>>(x, (const uint4 *)Wa, seg, pairs, n_seg, split, contrib);
-        GPC_LAUNCH_CHECK();
-    }
-    sp_centre_kernel<<<cdiv(n, 4 * SP_ROWS), 128, 0, st>>>(x, (const uint4 *)Wa, rowptr, contrib, n, residual, flags, y);
-    GPC_LAUNCH_CHECK();
-    return GPC_OK;
+    return sp_fwd_rows(x, Wa, seg, pairs, rowptr, n, n_entries, contrib, residual, flags, y, 0, n, stream);
+}
+// The same conv for the output rows [row0, row1) only (whole 8192-row blocks; row1 may be n): x, y, residual, contrib and the map
+// are the level's, rows outside the range are neither read as outputs nor written.  Used by the decoder's stage wavefront.
+extern "C" int gpc_spconv_sparse_fwd_rows(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
+                                          const uint32_t *rowptr, int64_t n, int64_t n_entries, float *contrib,
+                                          const float *residual, int flags, float *y, int64_t row0, int64_t row1, void *stream) {
+    return sp_fwd_rows(x, Wa, seg, pairs, rowptr, n, n_entries, contrib, residual, flags, y, row0, row1, stream);
 }

@@ -163,6 +163,13 @@ int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t *seg, const
                       int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                       void *stream);
 
+/* the v6d kernel (variant 48) for the output rows [row0, row1) of the level only (whole tiles; row1 may be n): the decoder codes a
+ * level as a wavefront over row chunks, stage i+1 of a chunk as soon as stage i of its 5^3 halo is decoded (pcc_utils.py:319-366 has
+ * the four stages strictly one after the other) */
+int gpc_spconv_fwd_v6_rows(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
+                           int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
+                           int64_t row0, int64_t row1, void *stream);
+
 /* row-tied kernel map ("rt8") + v7 conv (variant 50..): sub-tiles of 64 rows = 8 groups of 8 rows;
  * hdr[st*128 + k] = mask of groups with a neighbour at offset k; toff[st*126 + k] = first 8-entry tile of
  * (st,k) in `tiles` (u32 input rows, 0xFFFFFFFF = absent); accumulators stay in registers */
@@ -194,6 +201,11 @@ int gpc_kmap_sparse_fill(const int32_t *map, int64_t n, const uint32_t *seg, con
  * out; Wa = this conv's slice of gpc_spconv_pack_weights_frag; contrib = scratch of max(stragglers, 1) * 32 floats */
 int gpc_spconv_sparse_fwd(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs, const uint32_t *rowptr,
                           int64_t n, int64_t n_entries, float *contrib, const float *residual, int flags, float *y, void *stream);
+
+/* the same for the output rows [row0, row1) only (whole 8192-row blocks; row1 may be n) */
+int gpc_spconv_sparse_fwd_rows(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs, const uint32_t *rowptr,
+                               int64_t n, int64_t n_entries, float *contrib, const float *residual, int flags, float *y,
+                               int64_t row0, int64_t row1, void *stream);
 
 /* ---- the tcgen05 sparse conv (spconv_tc.cu, spconv_fmt.cu): the kernel the big octree levels run ---- */
 /* "split rows": an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits) -- a gathered

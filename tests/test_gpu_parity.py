@@ -547,6 +547,41 @@ def test_cli_file_roundtrip(env, tmp_path):
         assert drows[0]["num_points"] > 0 and np.array_equal(back, q)
 
 
+@pytest.mark.parametrize("kind", ["v6d", "sparse"])
+def test_decoder_wavefront(env, env_v6d, env_sparse, kind):
+    """The decoder's stage wavefront (chunks of rows, four range-decoder threads) against the stage-by-stage decode of the same
+    streams: identical geometry row for row; levels of every chunk count (ragged last chunk, levels that fail the halo check or are
+    too small fall back).  Both conv families that support row ranges."""
+    from gauspcc_b200.codec import GausPcgcCodec
+    from gauspcc_b200.synth import hac_like_cloud
+    src = (env_v6d if kind == "v6d" else env_sparse)["codec"]
+    codec = GausPcgcCodec(src.w, env["dev"], tile_rows=128 if kind == "v6d" else None)
+    codec.conv_variant = src.conv_variant
+    codec.sparse_min_rows, codec.sparse_max_density = src.sparse_min_rows, src.sparse_max_density
+    codec.wave_min_rows, codec.wave_chunk_rows = 1, 8192
+    for n, seed in ((120_000, 3), (30_000, 4)):
+        x = torch.tensor(hac_like_cloud(n, seed), dtype=torch.float32, device=codec.dev)
+        bx, bo, streams, _ = codec.encode(x)
+        codec.wave_decode = True
+        seen = []
+        orig = codec._decode_level_wavefront
+        codec._decode_level_wavefront = lambda *a, **k: (seen.append(a[2]), orig(*a, **k))[1]
+        try:
+            d_wave = codec.decode(bx, bo, streams)
+        finally:
+            codec._decode_level_wavefront = orig
+        codec.wave_decode = False
+        d_ref = codec.decode(bx, bo, streams)
+        assert torch.equal(d_wave, d_ref)
+        if n >= 100_000:
+            assert len(seen) >= 2 and max(seen) > 3 * 8192, seen          # the big levels did take the wavefront
+    # a corrupt stream must surface as an error or as wrong geometry, never as a hang
+    bad = list(streams)
+    bad[-1] = bad[-1][: len(bad[-1]) // 2]
+    codec.wave_decode = True
+    codec.decode(bx, bo, bad)
+
+
 def test_full_size_roundtrip_1m(env):
     """BASELINE config 2 size: lossless round trip, encoder == decoder CDFs (else the range decoder
     desynchronises and the geometry is garbage), teacher-forced decode == real decode."""
