@@ -162,6 +162,7 @@ struct FastWriter {
 // interval update needs ((span * c) >> 16).  Renormalisation shifts out the whole common prefix of low/high at once.
 #if defined(__x86_64__)
 #include <immintrin.h>
+#include <cstdlib>
 __attribute__((target("avx2"))) static inline int sym16_avx2(const u16 *row, u64 span, u64 num) {
     // prod[m] = row[m] * span for m = 0..15 (row[0] == 0), span = (span-1) + 1 with span-1 < 2^32
     const __m256i sm1 = _mm256_set1_epi64x((long long)(span - 1));
@@ -176,6 +177,18 @@ __attribute__((target("avx2"))) static inline int sym16_avx2(const u16 *row, u64
         s += 4 - __builtin_popcount((unsigned)_mm256_movemask_pd(_mm256_castsi256_pd(gt)));
     }
     return s - 1;                                                                       // entry 0 (== 0) always counts
+}
+// AVX-512: the 16 entries as two vectors of eight 64-bit products, compares straight into mask registers
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,avx2"))) static inline int sym16_avx512(const u16 *row, u64 span, u64 num) {
+    const __m512i sm1 = _mm512_set1_epi64((long long)(span - 1));
+    const __m512i nv = _mm512_set1_epi64((long long)num);
+    const __m256i r16 = _mm256_loadu_si256((const __m256i *)row);                       // 16 x u16 (entry 16 is not read)
+    const __m512i lo = _mm512_cvtepu16_epi64(_mm256_castsi256_si128(r16));
+    const __m512i hi = _mm512_cvtepu16_epi64(_mm256_extracti128_si256(r16, 1));
+    const __m512i plo = _mm512_add_epi64(_mm512_mul_epu32(lo, sm1), lo);
+    const __m512i phi = _mm512_add_epi64(_mm512_mul_epu32(hi, sm1), hi);
+    const unsigned le = (unsigned)_mm512_cmple_epu64_mask(plo, nv) | ((unsigned)_mm512_cmple_epu64_mask(phi, nv) << 8);
+    return __builtin_popcount(le) - 1;                                                   // entry 0 (== 0) always counts
 }
 #endif
 
@@ -208,8 +221,9 @@ static inline void ac_decode_start(AcDecState &st, const u8 *in, i64 in_len) {
     st.br.refill();
 }
 
-template <int LP /* 3, 5, 17 or 0 = any */, bool FAST>
+template <int LP /* 3, 5, 17 or 0 = any */, int ISA /* 0 = base, 1 = AVX2 + BMI2 + LZCNT, 2 = + AVX-512 */>
 static inline __attribute__((always_inline)) void ac_decode_body(AcDecState &state, const u16 *cdf, i64 n, int Lp_rt, u8 *sym) {
+    constexpr bool FAST = ISA >= 1;
     constexpr bool BINARY = LP == 3;
     const int Lp = LP ? LP : Lp_rt;
     BitReservoir br = state.br;                                                 // locals: kept in registers across the loop
@@ -234,7 +248,9 @@ static inline __attribute__((always_inline)) void ac_decode_body(AcDecState &sta
             p_hi = s ? (span << 16) : p1;
         } else {
 #if defined(__x86_64__)
-            if (FAST && LP == 17) {
+            if (ISA == 2 && LP == 17) {
+                s = sym16_avx512(row, span, num);
+            } else if (FAST && LP == 17) {
                 s = sym16_avx2(row, span, num);
             } else
 #endif
@@ -276,19 +292,27 @@ static inline __attribute__((always_inline)) void ac_decode_body(AcDecState &sta
     state.low = low; state.high = high; state.value = value;
 }
 GPC_AC_FAST_TARGET static void ac_decode_fast(AcDecState &st, const u16 *cdf, i64 n, int Lp, u8 *sym) {
-    if (Lp == 3) ac_decode_body<3, true>(st, cdf, n, Lp, sym);
-    else if (Lp == 5) ac_decode_body<5, true>(st, cdf, n, Lp, sym);
-    else if (Lp == 17) ac_decode_body<17, true>(st, cdf, n, Lp, sym);
-    else ac_decode_body<0, true>(st, cdf, n, Lp, sym);
+    if (Lp == 3) ac_decode_body<3, 1>(st, cdf, n, Lp, sym);
+    else if (Lp == 5) ac_decode_body<5, 1>(st, cdf, n, Lp, sym);
+    else if (Lp == 17) ac_decode_body<17, 1>(st, cdf, n, Lp, sym);
+    else ac_decode_body<0, 1>(st, cdf, n, Lp, sym);
 }
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,avx2,bmi,bmi2,lzcnt"))) static void ac_decode_512(AcDecState &st, const u16 *cdf, i64 n, u8 *sym) {
+    ac_decode_body<17, 2>(st, cdf, n, 17, sym);
+}
+#endif
 static void ac_decode_base(AcDecState &st, const u16 *cdf, i64 n, int Lp, u8 *sym) {
-    if (Lp == 3) ac_decode_body<3, false>(st, cdf, n, Lp, sym);
-    else if (Lp == 5) ac_decode_body<5, false>(st, cdf, n, Lp, sym);
-    else ac_decode_body<0, false>(st, cdf, n, Lp, sym);
+    if (Lp == 3) ac_decode_body<3, 0>(st, cdf, n, Lp, sym);
+    else if (Lp == 5) ac_decode_body<5, 0>(st, cdf, n, Lp, sym);
+    else ac_decode_body<0, 0>(st, cdf, n, Lp, sym);
 }
 static void ac_decode_dispatch(AcDecState &st, const u16 *cdf, i64 n, int Lp, u8 *sym) {
 #if defined(__x86_64__)
     static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+    static const bool wide = fast && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                             __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq") && !getenv("GPC_AC_NO_AVX512");
+    if (wide && Lp == 17) { ac_decode_512(st, cdf, n, sym); return; }
     if (fast) { ac_decode_fast(st, cdf, n, Lp, sym); return; }
 #endif
     ac_decode_base(st, cdf, n, Lp, sym);
