@@ -240,7 +240,7 @@ def main():
                "d2h_bytes_per_step": int(rows * 4 * 4 + rows * 2 * 28 + pts_host.numel() * 4),  # enc (c_low,c_high) words + dec CDF rows + result
                "enc_s": round(r["enc_time"], 4), "dec_s": round(d["dec_time"], 4), "bpp": round(r["bpp"], 3),
                "dec_host_ac_s": round(dec_stats.get("host_ac_s", 0.0), 4), "dec_gpu_wait_s": round(dec_stats.get("gpu_wait_s", 0.0), 4),
-               "dec_gpu_s": round(dec_stats.get("gpu_ms", 0.0) / 1e3, 4),
+               "dec_gpu_s": round(dec_stats.get("gpu_ms", 0.0) / 1e3, 4), "dec_wavefront_levels": int(dec_stats.get("wave_levels", 0)),
                "ac_threads": codec.pool._max_workers}
         assert pts_host.shape[0] == args.points
 

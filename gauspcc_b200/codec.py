@@ -813,6 +813,7 @@ class GausPcgcCodec:
         cur = Level(skeys, bo[perm.long()] if n0 else bo, n0)
         pin = self._pinned_dec                     # staging for CDF rows / symbols, kept across calls (grown geometrically)
         t_wait = t_ac = 0.0
+        n_wave = 0
         for g in range(0, len(streams), 4):
             n_child = self._popcount(cur.occ) if forced_occ is None else int(forced_occ[g // 4].shape[0])
             child, u = self.level_features(cur, n_child)
@@ -823,6 +824,7 @@ class GausPcgcCodec:
                 dw, da = self._decode_level_wavefront(u, child, n_child, streams[g:g + 4], occ)
                 t_wait += dw
                 t_ac += da
+                n_wave += 1
                 child.occ = occ
                 cur = child
                 continue
@@ -862,7 +864,10 @@ class GausPcgcCodec:
                        self._stream())
         self._seg_end()
         self._stream_h = None
-        self.last_stats = {"gpu_ms": self._seg_total_ms(), "launches": self.launches, "host_ac_s": t_ac, "gpu_wait_s": t_wait}
+        # host_ac_s: seconds inside the range decoder on the critical path (wavefront levels: the slowest of the four concurrent
+        # streams); gpu_ms: CUDA-event time of the GPU segments (wavefront levels: first launch to last, idle gaps included)
+        self.last_stats = {"gpu_ms": self._seg_total_ms(), "launches": self.launches, "host_ac_s": t_ac, "gpu_wait_s": t_wait,
+                           "wave_levels": n_wave}
         return out
 
 
