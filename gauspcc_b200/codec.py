@@ -506,8 +506,9 @@ class GausPcgcCodec:
             x = self.conv(t, b, km, residual=x, relu=True)
         return x
 
-    def level_features(self, parent: Level, n_child: int):
-        """pcc_utils.py:99-109 == :300-311: prior stack on S_d, expand, target embedding, target stack."""
+    def level_features(self, parent: Level, n_child: int, child_kmap: Optional[KMap] = None):
+        """pcc_utils.py:99-109 == :300-311: prior stack on S_d, expand, target embedding, target stack.
+        child_kmap: the kernel map of the child set if the caller has built it already (encoder)."""
         if parent.kmap is None:
             parent.kmap = self.build_kmap(parent.keys)
         f = self._empty((parent.n, 32), torch.float32)
@@ -517,7 +518,7 @@ class GausPcgcCodec:
         u0 = self._empty((n_child, 32), torch.float32)
         self._call("gpc_gather_parent_add_octant", _ptr(f), _ptr(cp), _ptr(ck), n_child, _ptr(self.w.target_emb), _ptr(u0),
                    self._stream())
-        child = Level(ck, None, n_child, self.build_kmap(ck))
+        child = Level(ck, None, n_child, child_kmap if child_kmap is not None else self.build_kmap(ck))
         # tcgen05 level: u is needed as fp32 rows (context embeddings) and as split rows (stage 0 conv input)
         u = self.res_stack(u0, W.TARGET_CONVS, child.kmap, final="both" if child.kmap.cta_rows else "f32")
         return child, u
@@ -611,12 +612,22 @@ class GausPcgcCodec:
             t = arena[start:start + nbytes]
             return t.view(dtype).view(shape)
 
-        for d in range(L):
+        # Kernel maps of all levels first, coarse -> fine: the order in which the decoder meets them, so that both sides take the same
+        # per-level kernel decisions (build_kmap's sparse switch is sticky along that order).  The levels themselves are then coded
+        # FINE -> COARSE: every level's CDFs depend on the ground truth only, and with the big levels first their host range coding
+        # (10 ms per stream at 1M rows) overlaps the GPU work of the remaining levels instead of trailing the last kernel.
+        if L:
+            for lv in levels:
+                if lv.kmap is None:
+                    lv.kmap = self.build_kmap(lv.keys)
+        level_futs = [[] for _ in range(L)]
+        if collect:
+            aux["child_keys"], aux["probs"], aux["cdfs"] = [None] * L, [None] * (4 * L), [None] * (4 * L)
+        for d in range(L - 1, -1, -1):
             parent, gt = levels[d], levels[d + 1]
-            child, u = self.level_features(parent, gt.n)
-            gt.kmap = child.kmap                       # same coordinate set: reuse for the next prior stack
+            child, u = self.level_features(parent, gt.n, child_kmap=gt.kmap)      # same coordinate set, same row order
             if collect:
-                aux.setdefault("child_keys", []).append(child.keys)
+                aux["child_keys"][d] = child.keys
             level_jobs = []
             for i in range(4):
                 A = W.STAGE_ALPHABETS[i]
@@ -629,13 +640,14 @@ class GausPcgcCodec:
                     lohi_h.copy_(lohi_d, non_blocking=True)
                     level_jobs.append(lohi_h)
                 if collect:
-                    aux["probs"].append(prob_d)
-                    aux["cdfs"].append(cdf_d)
+                    aux["probs"][4 * d + i] = prob_d
+                    aux["cdfs"][4 * d + i] = cdf_d
             if download:
                 ready = torch.cuda.Event()
                 ready.record(torch.cuda.current_stream(self.dev))
-                # host range coding of this level overlaps the GPU work of the finer levels
-                futs += [self.pool.submit(self._ac_encode_lohi, h.numpy().view(np.uint32), ready) for h in level_jobs]
+                # host range coding of this level overlaps the GPU work of the coarser levels
+                level_futs[d] = [self.pool.submit(self._ac_encode_lohi, h.numpy().view(np.uint32), ready) for h in level_jobs]
+        futs = [f for lf in level_futs for f in lf]            # stream order of the container: level-major coarse -> fine
         base = levels[0]
         base_xyz = self._empty((base.n, 3), torch.int32)
         self._call("gpc_unpack_keys_i32", _ptr(base.keys), base.n, _ptr(base_xyz), self._stream())
