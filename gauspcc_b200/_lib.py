@@ -27,6 +27,7 @@ SIGNATURES = {
     "gpc_last_error": (C.c_char_p, []),
     "gpc_version": (c_int, []),
     "gpc_launch_count": (C.c_uint64, []),
+    "gpc_copy_async": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "gpc_pack_keys_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_pack_keys_i32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_unpack_keys_i32": (c_int, [c_vp, c_i64, c_vp, c_vp]),

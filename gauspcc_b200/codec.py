@@ -133,6 +133,8 @@ class GausPcgcCodec:
         self.wave_decode = os.environ.get("GPC_WAVE_DECODE", "1") != "0"
         self.wave_min_rows = int(os.environ.get("GPC_WAVE_MIN_ROWS", 150_000))
         self.wave_chunk_rows = int(os.environ.get("GPC_WAVE_CHUNK_ROWS", 32768))
+        self.wave_first_rows = int(os.environ.get("GPC_WAVE_FIRST_ROWS", 8192))        # size / number of the small leading chunks
+        self.wave_first_chunks = int(os.environ.get("GPC_WAVE_FIRST_CHUNKS", 0))     # measured: small leading chunks cost more than they save (dec 0.242 vs 0.218 s)
         self._launch_base = 0
         self.last_stats: Dict[str, float] = {}
         self._segments: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
@@ -673,23 +675,41 @@ class GausPcgcCodec:
         km = child.kmap
         if not self.wave_decode or n < self.wave_min_rows or km.cta_rows:
             return False
-        if not (km.sparse or (getattr(km, "v6_variant", 0) == 48 and self.wave_chunk_rows % km.tile_rows == 0)):
+        if not (km.sparse or (getattr(km, "v6_variant", 0) == 48 and self.wave_chunk_rows % km.tile_rows == 0
+                              and self.wave_first_rows % km.tile_rows == 0)):
             return False
-        ch = self.wave_chunk_rows
-        nc = (n + ch - 1) // ch
+        if km.sparse and (self.wave_chunk_rows % 8192 or self.wave_first_rows % 8192):
+            return False
+        chunks = self._wave_chunks(n)
+        nc = len(chunks)
         if nc < 3:
             return False
         # every 5^3 neighbour of a row of chunk c must lie in chunks c-1 .. c+1: first z of chunk c minus last z of chunk c-2 >= 3
-        first = torch.arange(0, nc, device=self.dev) * ch
-        last = torch.clamp(first + ch, max=n) - 1
-        z = (child.keys[torch.cat([first, last])] >> 42).cpu().numpy()
+        idx = torch.tensor([r0 for r0, _ in chunks] + [r1 - 1 for _, r1 in chunks], device=self.dev)
+        z = (child.keys[idx] >> 42).cpu().numpy()
         zf, zl = z[:nc], z[nc:]
         return bool(np.all(zf[2:] - zl[:-2] >= 3))
 
+    def _wave_chunks(self, n: int) -> List[Tuple[int, int]]:
+        """Row chunks of a wavefront level: a few small ones first (stage i+1 starts three chunks behind stage i, so the first
+        chunks set how long the later stages' decoders wait at the start of a level), then wave_chunk_rows each."""
+        ch, small = self.wave_chunk_rows, self.wave_first_rows
+        sizes = [small] * self.wave_first_chunks if 0 < small < ch else []
+        out, r = [], 0
+        for sz in sizes:
+            if r + sz >= n:
+                break
+            out.append((r, r + sz))
+            r += sz
+        while r < n:
+            out.append((r, min(r + ch, n)))
+            r += ch
+        return out
+
     def _decode_level_wavefront(self, u, child: Level, n: int, streams: List[bytes], occ: torch.Tensor):
-        km, ch = child.kmap, self.wave_chunk_rows
-        nc = (n + ch - 1) // ch
-        chunks = [(c * ch, min((c + 1) * ch, n)) for c in range(nc)]
+        km = child.kmap
+        chunks = self._wave_chunks(n)
+        nc = len(chunks)
         u = u[0] if isinstance(u, tuple) else u
         Lps = [a + 1 for a in W.STAGE_ALPHABETS]
         # pinned staging: the four stages' CDF rows and symbols live at the same time
@@ -735,13 +755,22 @@ class GausPcgcCodec:
             except BaseException as e:          # noqa: BLE001 -- handed to the main thread, which re-raises
                 done_q.put((i, -1, e))
 
+        # the per-completion work below runs ~100 times per level: plain integer addresses instead of tensor views
+        call, sh = self._call, self._stream()
+        p_u, p_occ = u.data_ptr(), occ.data_ptr()
+        p_f = [0] + [t.data_ptr() for t in f[1:]]
+        p_t1 = [t.data_ptr() for t in t1]
+        p_cdf_d, p_cdf_h = [t.data_ptr() for t in cdf_d], [t.data_ptr() for t in cdf_h]
+        p_sym_d, p_sym_h = [t.data_ptr() for t in sym_d], [t.data_ptr() for t in sym_h]
+        heads = [tuple(_ptr(t) for t in self.w.head[i]) for i in range(4)]
+        embs = [0] + [_ptr(self.w.stage_emb[j]) for j in range(1, 4)]
+
         def emit_cdf(i: int, c: int):
             """head of stage i on chunk c -> D2H -> event for decoder thread i"""
             r0, r1 = chunks[c]
-            w1, b1, w2, b2 = self.w.head[i]
-            self._call("gpc_head_cdf", _ptr(t1[i][r0:r1]), r1 - r0, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i],
-                       _ptr(cdf_d[i][r0:r1]), _ptr(None), self._stream())
-            cdf_h[i][r0:r1].copy_(cdf_d[i][r0:r1], non_blocking=True)
+            w1, b1, w2, b2 = heads[i]
+            call("gpc_head_cdf", p_t1[i] + r0 * 128, r1 - r0, w1, b1, w2, b2, W.STAGE_ALPHABETS[i], p_cdf_d[i] + r0 * Lps[i] * 2, None, sh)
+            call("gpc_copy_async", p_cdf_h[i] + r0 * Lps[i] * 2, p_cdf_d[i] + r0 * Lps[i] * 2, (r1 - r0) * Lps[i] * 2, sh)
             ev = torch.cuda.Event()
             ev.record(stream)
             ev_q[i].put(ev)
@@ -764,14 +793,13 @@ class GausPcgcCodec:
                     raise err
                 pending -= 1
                 r0, r1 = chunks[c]
-                sym_d[i][r0:r1].copy_(sym_h[i][r0:r1], non_blocking=True)
-                self._call("gpc_merge_symbol", _ptr(occ[r0:r1]), r1 - r0, STAGE_SHIFT[i], _ptr(sym_d[i][r0:r1]), self._stream())
+                call("gpc_copy_async", p_sym_d[i] + r0, p_sym_h[i] + r0, r1 - r0, sh)
+                call("gpc_merge_symbol", p_occ + r0, r1 - r0, STAGE_SHIFT[i], p_sym_d[i] + r0, sh)
                 if i == 3:
                     continue
                 j = i + 1
                 k0, k1 = W.stage_convs(j)
-                self._call("gpc_add_ctx_embed", _ptr(u[r0:r1]), _ptr(occ[r0:r1]), CTX_SHIFT[j], _ptr(self.w.stage_emb[j]), r1 - r0,
-                           _ptr(f[j][r0:r1]), self._stream())
+                call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0, p_f[j] + r0 * 128, sh)
                 last = c == nc - 1
                 for cc in ([c - 1] if c >= 1 else []) + ([c] if last else []):          # first conv: inputs of chunks cc-1 .. cc+1 are there
                     self.conv(f[j], k0, km, relu=True, out=t0[j], rows=chunks[cc])

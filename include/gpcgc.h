@@ -51,6 +51,8 @@ const char *gpc_last_error(void);
 int gpc_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t gpc_launch_count(void);
+/* cudaMemcpyAsync(cudaMemcpyDefault) on `stream`: device or pinned host pointers on either side */
+int gpc_copy_async(void *dst, const void *src, int64_t bytes, void *stream);
 
 /* key transform for sorting: compact = ((z-minz)<<sz) | ((y-miny)<<sy) | (x-minx) on the biased
  * 21-bit fields; digits of `compact` are what the radix sort consumes (fewer passes than 63 bits) */
