@@ -133,6 +133,9 @@ class GausPcgcCodec:
         self.wave_decode = os.environ.get("GPC_WAVE_DECODE", "1") != "0"
         self.wave_min_rows = int(os.environ.get("GPC_WAVE_MIN_ROWS", 150_000))
         self.wave_chunk_rows = int(os.environ.get("GPC_WAVE_CHUNK_ROWS", 32768))
+        self.wave_streams = os.environ.get("GPC_WAVE_STREAMS", "1") != "0"
+        self._wave_side: Optional[list] = None
+        self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
         self.wave_first_rows = int(os.environ.get("GPC_WAVE_FIRST_ROWS", 8192))        # size / number of the small leading chunks
         self.wave_first_chunks = int(os.environ.get("GPC_WAVE_FIRST_CHUNKS", 0))     # measured: small leading chunks cost more than they save (dec 0.242 vs 0.218 s)
         self._launch_base = 0
@@ -755,8 +758,18 @@ class GausPcgcCodec:
             except BaseException as e:          # noqa: BLE001 -- handed to the main thread, which re-raises
                 done_q.put((i, -1, e))
 
+        # One CUDA stream per stage on the dense levels: a 32 K-row chunk is 256 one-warp CTAs, a seventh of the GPU, and a chunk's conv
+        # lasts as long as its slowest warp's chain of tiles, so on one stream the three stages' chunk work (0.9 ms per chunk index at
+        # 442 K rows) outlasted the decoders (0.55 ms).  Stage j's work runs on stream j; what it reads from other stages (symbols,
+        # occupancy bits) has reached the host before it is enqueued, and at any moment the stages work on disjoint chunks.  The
+        # sparse levels (decoder-bound, and their convs share the level's contribution scratch) stay on the one stream.
+        multi = self.wave_streams and not km.sparse
+        if multi and self._wave_side is None:
+            self._wave_side = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+        S = [stream] + (self._wave_side if multi else [stream] * 3)
+        SH = [st_.cuda_stream for st_ in S]
         # the per-completion work below runs ~100 times per level: plain integer addresses instead of tensor views
-        call, sh = self._call, self._stream()
+        call = self._call
         p_u, p_occ = u.data_ptr(), occ.data_ptr()
         p_f = [0] + [t.data_ptr() for t in f[1:]]
         p_t1 = [t.data_ptr() for t in t1]
@@ -769,10 +782,10 @@ class GausPcgcCodec:
             """head of stage i on chunk c -> D2H -> event for decoder thread i"""
             r0, r1 = chunks[c]
             w1, b1, w2, b2 = heads[i]
-            call("gpc_head_cdf", p_t1[i] + r0 * 128, r1 - r0, w1, b1, w2, b2, W.STAGE_ALPHABETS[i], p_cdf_d[i] + r0 * Lps[i] * 2, None, sh)
-            call("gpc_copy_async", p_cdf_h[i] + r0 * Lps[i] * 2, p_cdf_d[i] + r0 * Lps[i] * 2, (r1 - r0) * Lps[i] * 2, sh)
+            call("gpc_head_cdf", p_t1[i] + r0 * 128, r1 - r0, w1, b1, w2, b2, W.STAGE_ALPHABETS[i], p_cdf_d[i] + r0 * Lps[i] * 2, None, SH[i])
+            call("gpc_copy_async", p_cdf_h[i] + r0 * Lps[i] * 2, p_cdf_d[i] + r0 * Lps[i] * 2, (r1 - r0) * Lps[i] * 2, SH[i])
             ev = torch.cuda.Event()
-            ev.record(stream)
+            ev.record(S[i])
             ev_q[i].put(ev)
 
         workers = [self.pool.submit(worker, i) for i in range(4)]
@@ -784,6 +797,11 @@ class GausPcgcCodec:
             self.conv(t0[0], c1, km, out=t1[0])
             for c in range(nc):
                 emit_cdf(0, c)
+            if multi:
+                ready = torch.cuda.Event()
+                ready.record(stream)               # u, the kernel map, the zeroed occupancy: all produced on the main stream
+                for st_ in S[1:]:
+                    st_.wait_event(ready)
             pending = 4 * nc
             while pending:
                 tb = time.perf_counter()
@@ -793,11 +811,12 @@ class GausPcgcCodec:
                     raise err
                 pending -= 1
                 r0, r1 = chunks[c]
+                j = min(i + 1, 3)
+                sh = self._stream_h = SH[j]           # everything this completion triggers goes to the next stage's stream
                 call("gpc_copy_async", p_sym_d[i] + r0, p_sym_h[i] + r0, r1 - r0, sh)
                 call("gpc_merge_symbol", p_occ + r0, r1 - r0, STAGE_SHIFT[i], p_sym_d[i] + r0, sh)
                 if i == 3:
                     continue
-                j = i + 1
                 k0, k1 = W.stage_convs(j)
                 call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0, p_f[j] + r0 * 128, sh)
                 last = c == nc - 1
@@ -813,11 +832,19 @@ class GausPcgcCodec:
                 q.put(None)                       # let the decoder threads go
             raise
         finally:
+            self._stream_h = SH[0]
+            if multi:
+                for st_ in S[1:]:                 # the level's buffers go back to the main stream's allocator only after the side streams
+                    done = torch.cuda.Event()
+                    done.record(st_)
+                    stream.wait_event(done)
             for w_ in workers:
                 try:
                     w_.result()
                 except BaseException:             # noqa: BLE001 -- the first error is already on its way up
                     pass
+        if self.wave_log is not None:
+            self.wave_log.append({"rows": n, "chunks": nc, "sparse": bool(km.sparse), "ac_s": [round(v, 4) for v in ac_s]})
         return t_wait, max(ac_s)
 
     def decode(self, base_xyz: np.ndarray, base_occ: np.ndarray, streams: List[bytes], scale: float = 1.0,
