@@ -135,6 +135,7 @@ class GausPcgcCodec:
         self.wave_chunk_rows = int(os.environ.get("GPC_WAVE_CHUNK_ROWS", 32768))
         self.wave_streams = os.environ.get("GPC_WAVE_STREAMS", "1") != "0"
         self._wave_side: Optional[list] = None
+        self._wave_buf: Optional[torch.Tensor] = None
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
         self.wave_first_rows = int(os.environ.get("GPC_WAVE_FIRST_ROWS", 8192))        # size / number of the small leading chunks
         self.wave_first_chunks = int(os.environ.get("GPC_WAVE_FIRST_CHUNKS", 0))     # measured: small leading chunks cost more than they save (dec 0.242 vs 0.218 s)
@@ -729,9 +730,15 @@ class GausPcgcCodec:
             off += (n + 63) // 64 * 64
         cdf_d = [self._empty((n, Lp), torch.int16) for Lp in Lps]
         sym_d = [self._empty((n,), torch.uint8) for _ in range(4)]
-        f = [None] + [self._empty((n, 32), torch.float32) for _ in range(3)]
-        t0 = [self._empty((n, 32), torch.float32) for _ in range(4)]
-        t1 = [self._empty((n, 32), torch.float32) for _ in range(4)]
+        # eleven level-sized feature arrays, carved from one buffer the codec keeps (grown geometrically): scenes of other sizes reuse it
+        # instead of sending the caching allocator back to cudaMalloc, and no block returns to the allocator while side streams use it
+        if self._wave_buf is None or self._wave_buf.numel() < 11 * n * 32:
+            self._wave_buf = None
+            self._wave_buf = torch.empty(int(11 * n * 32 * 1.3) + 1024, dtype=torch.float32, device=self.dev)
+        carve = [self._wave_buf[k * n * 32:(k + 1) * n * 32].view(n, 32) for k in range(11)]
+        f = [None] + carve[0:3]
+        t0 = carve[3:7]
+        t1 = carve[7:11]
         stream = torch.cuda.current_stream(self.dev)
         ev_q = [queue.Queue() for _ in range(4)]
         done_q: "queue.Queue" = queue.Queue()
