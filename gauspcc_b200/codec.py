@@ -133,6 +133,7 @@ class GausPcgcCodec:
         self.wave_decode = os.environ.get("GPC_WAVE_DECODE", "1") != "0"
         self.wave_min_rows = int(os.environ.get("GPC_WAVE_MIN_ROWS", 150_000))
         self.wave_chunk_rows = int(os.environ.get("GPC_WAVE_CHUNK_ROWS", 32768))
+        self.wave_plane_lag = os.environ.get("GPC_WAVE_PLANE_LAG", "1") != "0"   # stage i+1 trails stage i by planes, not by two chunks
         self.wave_streams = os.environ.get("GPC_WAVE_STREAMS", "1") != "0"
         self._wave_side: Optional[list] = None
         self._wave_buf: Optional[torch.Tensor] = None
@@ -686,6 +687,8 @@ class GausPcgcCodec:
             return False
         chunks = self._wave_chunks(n)
         nc = len(chunks)
+        if self.wave_plane_lag:
+            return nc >= 2                  # the plan (_wave_plan) is valid for any geometry; it degenerates to stage by stage at worst
         if nc < 3:
             return False
         # every 5^3 neighbour of a row of chunk c must lie in chunks c-1 .. c+1: first z of chunk c minus last z of chunk c-2 >= 3
@@ -693,6 +696,29 @@ class GausPcgcCodec:
         z = (child.keys[idx] >> 42).cpu().numpy()
         zf, zl = z[:nc], z[nc:]
         return bool(np.all(zf[2:] - zl[:-2] >= 3))
+
+    def _wave_plan(self, keys: torch.Tensor, n: int, chunks: List[Tuple[int, int]], tile: int):
+        """Row ranges of the wavefront with a lag of PLANES instead of chunks.  Rows are sorted by (z, y, x); if stage i is known for
+        the rows < e, the first conv of stage i+1 is exact for every row whose 5^3 neighbours are all < e: the planes z <= z[e] - 3,
+        i.e. the rows before the first row of plane z[e] - 2 (rounded down to the conv's tile height); the second conv, likewise, for
+        the rows two more planes back; those rows' CDFs go to decoder i+1.  Returns per stage the piece ends E[i][c] (stage 0: the
+        chunks) and the first-conv ends CA[i][c], as Python ints; piece c of stage i+1 is released by piece c of stage i."""
+        dev = self.dev
+        nn = torch.tensor(n, device=dev)
+
+        def lag(end: torch.Tensor) -> torch.Tensor:
+            zf = keys[end.clamp(max=n - 1)] >> 42                                  # plane of the first row that is not valid yet
+            out = torch.searchsorted(keys, (zf - 2) << 42) // tile * tile          # smallest key of plane zf - 2 -> its first row
+            return torch.where(end >= n, nn, out)
+
+        E = [torch.tensor([r1 for _, r1 in chunks], device=dev, dtype=torch.int64)]
+        CA = [E[0]]
+        for _ in range(3):
+            ca = lag(E[-1])
+            CA.append(ca)
+            E.append(lag(ca))
+        flat = torch.stack(E + CA).cpu().tolist()
+        return flat[:4], flat[4:]
 
     def _wave_chunks(self, n: int) -> List[Tuple[int, int]]:
         """Row chunks of a wavefront level: a few small ones first (stage i+1 starts three chunks behind stage i, so the first
@@ -752,7 +778,10 @@ class GausPcgcCodec:
                 buf = (C.c_char * max(len(data), 1)).from_buffer_copy(data if len(data) else b"\0")
                 _lib.check(self.lib.gpc_ac_decode_begin_h(C.cast(st, C.c_void_p), C.cast(buf, C.c_void_p), len(data)), "gpc_ac_decode_begin_h")
                 cdf_np, sym_np = cdf_h[i].numpy().view(np.uint16), sym_h[i].numpy()
-                for c, (r0, r1) in enumerate(chunks):
+                for c, (r0, r1) in enumerate(P[i]):
+                    if r1 <= r0:                       # empty piece (plane lag): nothing to decode, but the next stage's step c is due
+                        done_q.put((i, c, None))
+                        continue
                     ev = ev_q[i].get()
                     if ev is None:
                         return
@@ -785,9 +814,9 @@ class GausPcgcCodec:
         heads = [tuple(_ptr(t) for t in self.w.head[i]) for i in range(4)]
         embs = [0] + [_ptr(self.w.stage_emb[j]) for j in range(1, 4)]
 
-        def emit_cdf(i: int, c: int):
-            """head of stage i on chunk c -> D2H -> event for decoder thread i"""
-            r0, r1 = chunks[c]
+        def emit_cdf(i: int, c: int, rng: Optional[Tuple[int, int]] = None):
+            """head of stage i on chunk c (or the row range rng) -> D2H -> event for decoder thread i"""
+            r0, r1 = chunks[c] if rng is None else rng
             w1, b1, w2, b2 = heads[i]
             call("gpc_head_cdf", p_t1[i] + r0 * 128, r1 - r0, w1, b1, w2, b2, W.STAGE_ALPHABETS[i], p_cdf_d[i] + r0 * Lps[i] * 2, None, SH[i])
             call("gpc_copy_async", p_cdf_h[i] + r0 * Lps[i] * 2, p_cdf_d[i] + r0 * Lps[i] * 2, (r1 - r0) * Lps[i] * 2, SH[i])
@@ -795,6 +824,12 @@ class GausPcgcCodec:
             ev.record(S[i])
             ev_q[i].put(ev)
 
+        plane = self.wave_plane_lag
+        if plane:
+            E, CA = self._wave_plan(child.keys, n, chunks, 8192 if km.sparse else km.tile_rows)
+            P = [[(E[i][c - 1] if c else 0, E[i][c]) for c in range(nc)] for i in range(4)]
+        else:
+            P = [chunks] * 4
         workers = [self.pool.submit(worker, i) for i in range(4)]
         t_wait = 0.0
         try:
@@ -817,9 +852,27 @@ class GausPcgcCodec:
                 if err is not None:
                     raise err
                 pending -= 1
-                r0, r1 = chunks[c]
                 j = min(i + 1, 3)
                 sh = self._stream_h = SH[j]           # everything this completion triggers goes to the next stage's stream
+                if plane:
+                    r0, r1 = P[i][c]
+                    if r1 > r0:
+                        call("gpc_copy_async", p_sym_d[i] + r0, p_sym_h[i] + r0, r1 - r0, sh)
+                        call("gpc_merge_symbol", p_occ + r0, r1 - r0, STAGE_SHIFT[i], p_sym_d[i] + r0, sh)
+                    if i == 3:
+                        continue
+                    k0, k1 = W.stage_convs(j)
+                    if r1 > r0:
+                        call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0, p_f[j] + r0 * 128, sh)
+                    a0, a1 = (CA[j][c - 1] if c else 0), CA[j][c]
+                    if a1 > a0:
+                        self.conv(f[j], k0, km, relu=True, out=t0[j], rows=(a0, a1))
+                    q0, q1 = P[j][c]
+                    if q1 > q0:
+                        self.conv(t0[j], k1, km, out=t1[j], rows=(q0, q1))
+                        emit_cdf(j, c, (q0, q1))
+                    continue
+                r0, r1 = chunks[c]
                 call("gpc_copy_async", p_sym_d[i] + r0, p_sym_h[i] + r0, r1 - r0, sh)
                 call("gpc_merge_symbol", p_occ + r0, r1 - r0, STAGE_SHIFT[i], p_sym_d[i] + r0, sh)
                 if i == 3:

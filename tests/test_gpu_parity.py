@@ -547,8 +547,9 @@ def test_cli_file_roundtrip(env, tmp_path):
         assert drows[0]["num_points"] > 0 and np.array_equal(back, q)
 
 
+@pytest.mark.parametrize("plane", [True, False])
 @pytest.mark.parametrize("kind", ["v6d", "sparse"])
-def test_decoder_wavefront(env, env_v6d, env_sparse, kind):
+def test_decoder_wavefront(env, env_v6d, env_sparse, kind, plane):
     """The decoder's stage wavefront (chunks of rows, four range-decoder threads) against the stage-by-stage decode of the same
     streams: identical geometry row for row; levels of every chunk count (ragged last chunk, levels that fail the halo check or are
     too small fall back).  Both conv families that support row ranges."""
@@ -559,6 +560,7 @@ def test_decoder_wavefront(env, env_v6d, env_sparse, kind):
     codec.conv_variant = src.conv_variant
     codec.sparse_min_rows, codec.sparse_max_density = src.sparse_min_rows, src.sparse_max_density
     codec.wave_min_rows, codec.wave_chunk_rows = 1, 8192
+    codec.wave_plane_lag = plane                       # stage i+1 trails stage i by planes (default) / by two chunks
     if kind == "sparse":                               # small leading chunks, then bigger ones
         codec.wave_chunk_rows, codec.wave_first_rows, codec.wave_first_chunks = 16384, 8192, 2
     for n, seed in ((120_000, 3), (30_000, 4)):
