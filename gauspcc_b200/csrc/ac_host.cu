@@ -270,6 +270,24 @@ static inline __attribute__((always_inline)) void ac_decode_body(AcDecState &sta
         if (br.have < 40) br.refill();
         low = (u32)((u64)low << sh);
         high = (u32)(((u64)high << sh) | ((1ull << sh) - 1ull));
+        if (!BINARY) {
+            // prefix shift and underflow shifts with ONE read of sh + u bits: the bits of the two steps are consecutive in the stream and
+            // the underflow flip touches bit 31 only, so value'' = ((value << (sh + u)) | bits) ^ (u ? 2^31 : 0)   (mod 2^32)
+            const int ul = clz32(~(low << 1)), uh = clz32(high << 1);
+            int u = ul < uh ? ul : uh;
+            u = u > 31 ? 31 : u;                                                // keeps the shifts defined (low = 01..1, high = 10..0 for 31 bits cannot both hold)
+            const int t = sh + u;
+            low = (low << u) & 0x7FFFFFFFu;
+            high = (high << u) | 0x80000000u | ((1u << u) - 1u);
+            if (__builtin_expect(t <= 32, 1)) {
+                value = ((u32)((u64)value << t) | br.take(t)) ^ (u ? 0x80000000u : 0u);
+            } else {                                                            // > 32 bits at once: the two reads of the plain form
+                value = (u32)((u64)value << sh) | br.take(sh);
+                if (br.have < 40) br.refill();
+                value = ((value << u) ^ 0x80000000u) | br.take(u);
+            }
+            continue;
+        }
         value = (u32)((u64)value << sh) | br.take(sh);
         if (BINARY) {
             while (low >= 0x40000000u && high < 0xC0000000u) {                  // rare here
