@@ -668,14 +668,14 @@ class GausPcgcCodec:
                            "d2h_bytes": cursor, "n_unique": int(leaf.shape[0])}
         return base_xyz_h, base_occ_h, streams, aux
 
-    # ------------------------------------------------------------------ decode
     # ------------------------------------------------------------------ decoder: the four stages of a level as a wavefront
     # pcc_utils.py:319-366 decodes a level stage by stage: CDFs of stage i for ALL rows -> range decoder (one serial stream) -> symbols
     # -> stage i+1.  The dependency is local, though: stage i+1 of a row needs the stage-i symbols of the rows within two 5^3 convs
-    # of it, and rows are sorted by (z, y, x).  So the level is cut into chunks of rows; as soon as stage i is decoded for chunks
-    # <= c + 2 the GPU computes the stage-(i+1) CDFs of chunk c, and the four stage streams decode on four host threads, each a few
-    # chunks behind the previous one.  Same kernels, same sums, same bitstream; the serial range decoder (0.28 s of a 0.35 s decode
-    # at 1M anchors) overlaps with itself.
+    # of it, and rows are sorted by (z, y, x).  So stage 0 is handed to its decoder in chunks of rows; whenever decoder i reports a
+    # piece, the GPU computes the stage-(i+1) CDFs of every row whose neighbourhood is now decoded (_wave_plan: a lag of a few
+    # z planes; wave_plane_lag = False: the older scheme with a lag of two whole chunks), and the four stage streams decode on four
+    # host threads, one piece behind each other.  Same kernels, same sums, same bitstream; the serial range decoder (0.28 s of a
+    # 0.35 s decode at 1M anchors) overlaps with itself.
     def _wave_ok(self, child: Level, n: int) -> bool:
         km = child.kmap
         if not self.wave_decode or n < self.wave_min_rows or km.cta_rows:
