@@ -266,7 +266,7 @@ def main():
                          # algorithmic bytes (187.9 MB) = 0.94 (profiles/r01_spconv_v6_ncu_summary.md); scaled to the average launch of this run
                          "traffic": round(0.94 * conv_bytes / max(conv_launches, 1)),
                          "note": "all sparse-conv launches of the step; the dominant kernel (spconv_fwd_v6d<128>, 56 % of the step) is not HBM-bound: "
-                                 "L1/shared path 59 %, issue 36 %, HMMA pipe 27 %, 10 of 12 resident warps per SM waiting on L2 latency (ncu); "
+                                 "L1/shared path 69 %, issue 41 %, HMMA pipe 30 %, 10 of 12 resident warps per SM, latency-bound (ncu, final capture); "
                                  "see DESIGN.md 5",
                          "launches": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4), "event_pairs": len(prof),
                          "share_of_step": round(conv_ms / ms, 4), "tflops_fp32": round(conv_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms else 0},
