@@ -952,6 +952,7 @@ class GausPcgcCodec:
                 t_wait += dw
                 t_ac += da
                 n_wave += 1
+                pin = self._pinned_dec                 # the wavefront may have grown the staging buffer
                 child.occ = occ
                 cur = child
                 continue
