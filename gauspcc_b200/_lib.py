@@ -76,6 +76,9 @@ SIGNATURES = {
     "gpc_rows_join": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "gpc_spconv_fwd_tc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
     "gpc_debug_conv_tc_profile": (c_int, [c_vp, c_int]),
+    "gpc_debug_conv_um_profile": (c_int, [c_vp, c_int]),
+    "gpc_spconv_pack_weights_um": (c_int, [c_vp, c_int, c_vp, c_vp]),
+    "gpc_spconv_fwd_um": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),

@@ -311,6 +311,10 @@ extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows,
     if (n <= 0) return GPC_OK;
     // padded streams: entries not written below stay INVALID (all ones)
     if (pairs && n_entries > 0) GPC_CUDA_CHECK(cudaMemsetAsync(pairs, 0xFF, (size_t)n_entries * 8, as_stream(stream)));
+    if (pair_nbr && n_entries > 0) {               // split arrays: padding = row 0xFFFFFFFF (out of bounds for the TMA gather: zero fill) / 0xFFFF
+        GPC_CUDA_CHECK(cudaMemsetAsync(pair_nbr, 0xFF, (size_t)n_entries * 4, as_stream(stream)));
+        GPC_CUDA_CHECK(cudaMemsetAsync(pair_row, 0xFF, (size_t)n_entries * 2, as_stream(stream)));
+    }
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
     cudaStream_t st = as_stream(stream);
     if (tile_rows == 8) kmap_pairs_fill_sub_kernel<8><<<cdiv(tiles, 16), 128, 0, st>>>(map, n, tiles, seg, pair_nbr, pair_row, pairs);
