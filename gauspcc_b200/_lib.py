@@ -77,6 +77,7 @@ SIGNATURES = {
     "gpc_spconv_fwd_tc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
     "gpc_debug_conv_tc_profile": (c_int, [c_vp, c_int]),
     "gpc_debug_conv_um_profile": (c_int, [c_vp, c_int]),
+    "gpc_kmap_row_offsets": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "gpc_spconv_pack_weights_um": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "gpc_spconv_fwd_um": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -47,6 +47,11 @@ __device__ __forceinline__ void tmem_ld16(u32 taddr, u32 (&d)[16]) {
                  : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(u32 taddr, u32 (&d)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]) : "r"(taddr) : "memory");
+}
+
 // ---- mbarrier
 #ifndef TC_POLL_SLEEP_NS
 #define TC_POLL_SLEEP_NS 0
@@ -67,6 +72,42 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
         if (TC_POLL_SLEEP_NS) __nanosleep(TC_POLL_SLEEP_NS);
+    }
+    __trap();
+}
+
+// try_wait with an explicit suspend-time hint: the warp sleeps in hardware until the phase completes or the hint (ns) runs out
+__device__ __forceinline__ void mbar_wait_hint(u32 bar, u32 parity) {
+#pragma unroll 1
+    for (u32 spins = 0; spins < (1u << 20); ++spins) {
+        u32 done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// pure polling (mbarrier.test_wait never suspends the warp): for the roles on the critical path of a short hand-off
+__device__ __forceinline__ void mbar_wait_spin(u32 bar, u32 parity) {
+#pragma unroll 1
+    for (u32 spins = 0; spins < (1u << 26); ++spins) {
+        u32 done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// the same with a back-off between polls: for roles that wait long (a spinning warp's polls share the memory-instruction queue of its
+// scheduler with the loads and stores of the warps that do the work)
+template <int NS> __device__ __forceinline__ void mbar_wait_backoff(u32 bar, u32 parity) {
+#pragma unroll 1
+    for (u32 spins = 0; spins < (1u << 24); ++spins) {
+        u32 done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(NS);
     }
     __trap();
 }

@@ -228,19 +228,22 @@ int gpc_spconv_fwd_tc(const void *xs, const void *Wc, const uint32_t *seg, const
                       int cta_rows, const void *residual, int flags, float *y, void *ys, int profile, void *stream);
 int gpc_debug_conv_tc_profile(unsigned long long *out_h, int reset);
 
-/* ---- the TMA + tcgen05 sparse conv of the big levels (spconv_um.cu) ----
+/* ---- the tcgen05 sparse conv of the big levels (spconv_um.cu) ----
  * y[o,:] = act( sum_k W[k]^T xs[nbr_k(o),:] (+ residual[o,:]) ).  Transposed formulation: per (tile of tile_rows output rows, offset k)
  * the pairs are the N dimension of tcgen05.mma (chunks of 16..64/128 pairs), W[k]^T (bf16 hi | lo) is the A operand in tensor
- * memory, the rows gathered by TMA tile::gather4 (128 B swizzle) are the B operand in shared memory, D in tensor memory; the
- * epilogue adds every pair to its output row's fp32 sum in shared memory, offsets ascending (one fixed summation order).
- * xs = split rows; Wp = this conv's slice of gpc_spconv_pack_weights_um ([125][32 co][128 B]); seg / pair_nbr / pair_row = the
- * pair stream (gpc_kmap_pairs_*) built with tile_rows = 512 or 1024 and pad = 16.  Outputs y (fp32 rows) and / or ys (split rows).
- * Only the output rows [row0, row1) are computed (whole tiles; row1 <= 0 or >= n: to the end): the decoder wavefront. */
-#define GPC_CONV_TMA_GATHER 512   /* flags bit: gather the rows with TMA tile::gather4 instead of cp.async (A/B; profiles/r02_conv_um.md) */
+ * memory, the gathered rows (cp.async into 128 B-swizzled tiles; TMA tile loads for the centre offset) are the B operand in shared
+ * memory, D in tensor memory; the epilogue adds every pair to its output row's fp32 sum in shared memory, offsets ascending (one
+ * fixed summation order per row).
+ * xs = split rows; Wp = this conv's slice of gpc_spconv_pack_weights_um ([125][32 co][128 B]); seg / pair_nbr = the pair stream
+ * (gpc_kmap_pairs_*) built with tile_rows = 512 or 1024 and pad = 16, pair_off = gpc_kmap_row_offsets(pair_row).  Outputs y (fp32
+ * rows) and / or ys (split rows).  Only the output rows [row0, row1) are computed (whole tiles; row1 <= 0 or >= n: to the end):
+ * the decoder wavefront.  flags: GPC_CONV_RELU, GPC_CONV_RES_SPLIT, GPC_CONV_PROFILE. */
 #define GPC_CONV_PROFILE 256   /* flags bit: run the instrumented build (per-role cycle counters, gpc_debug_conv_um_profile) */
 int gpc_debug_conv_um_profile(unsigned long long *out_h, int reset);
 int gpc_spconv_pack_weights_um(const float *W, int n_kernels, void *Wp, void *stream);
-int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr, const uint16_t *pair_row,
+/* pair_row (row within the tile, 0xFFFF = padding) -> byte offset of the pair's accumulator row (row * 128; padding -> dummy row) */
+int gpc_kmap_row_offsets(const uint16_t *pair_row, int64_t n_entries, int tile_rows, uint32_t *pair_off, void *stream);
+int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr, const uint32_t *pair_off,
                       int64_t n, int tile_rows, const void *residual, int flags, float *y, void *ys, int64_t row0, int64_t row1,
                       void *stream);
 

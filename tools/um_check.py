@@ -67,13 +67,15 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms6 = e0.elapsed_time(e1) / reps
         err6 = float((y6.double() - torch.relu((ref - xj.double().new_zeros(1)) + res.double())).abs().max())
-        for tr, tmag in [(t_, g_) for t_ in tiles for g_ in [int(v) for v in os.environ.get("UM_TMA", "0,1").split(",")]]:
-            gflag = 512 if tmag else 0
+        for tr in tiles:
+            tmag, gflag = 0, 0
             km = codec._pair_stream(dense, n, tr, 16, True)
             km._fill()
+            poff = torch.empty((max(km.n_pairs, 1),), dtype=torch.int32, device=dev)
+            _lib.check(lib.gpc_kmap_row_offsets(_ptr(km.pair_row), km.n_pairs, tr, _ptr(poff), st), "row_offsets")
             y = torch.full((n, 32), float("nan"), device=dev)
             ys = torch.zeros((n, 32), dtype=torch.int32, device=dev)
-            args = (_ptr(xs), _ptr(wp[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_row), n, tr, _ptr(res), 1 | gflag, _ptr(y), _ptr(ys), 0, 0, st)
+            args = (_ptr(xs), _ptr(wp[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(poff), n, tr, _ptr(res), 1 | gflag, _ptr(y), _ptr(ys), 0, 0, st)
             rc = lib.gpc_spconv_fwd_um(*args)
             _lib.check(rc, "um")
             torch.cuda.synchronize()
@@ -105,7 +107,7 @@ def main():
                 buf = (C.c_uint64 * 16)()
                 lib.gpc_debug_conv_um_profile(C.cast(buf, C.c_void_p), 1)
                 ch, ctas = max(buf[11], 1), max(buf[15], 1)
-                names = ["p.empty_g", "p.issue", "m.full_w", "m.full_g", "m.empty_d", "m.issue", "p.wait+arrive", "-", "e.full_d", "e.range", "e.ld+rmw"]
+                names = ["e.items", "p.empty_g", "p.issue", "m.full_w", "m.full_g", "m.empty_d", "m.issue", "e.loop", "e.full_d", "e.ldtm_issue", "e.rmw"]
                 print(f"   prof tile={tr} tma={tmag}: chunks/cta={ch / ctas:.0f} " + " ".join(f"{nm}={buf[i] / ch:.0f}" for i, nm in enumerate(names))
                       + f" | per cta: total={buf[12] / ctas:.0f} setup={buf[13] / ctas:.0f} writeout={buf[14] / ctas:.0f}", flush=True)
             print(f"n={n:8d} p/r={n_pairs_real / n:5.1f} tile={tr:4d} tma={tmag} entries/pairs={km.n_pairs / max(n_pairs_real, 1):.2f} "
