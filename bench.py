@@ -258,8 +258,7 @@ def main():
                        "parallelism": f"scene-sharded x{world}", "wall_ms_per_step": round(t_wall * 1e3 / args.steps, 2)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": ("spconv_fwd_v6d / v6 (mma.sync)" if codec.conv_variant < 100 else "spconv_tc (tcgen05) + spconv_fwd_v6") +
-                                   " + sp_centre / sp_straggler on the sparse big levels, variant %d" % codec.conv_variant,
+            "roofline": {"kernel": "spconv_um (tcgen05) + sp_centre / sp_straggler + spconv_fwd_v6",
                          "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                          "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                          # dram__bytes_read+write of the profiled launch (442 133-row level, spconv_fwd_v6d<128>: 145.4 + 31.4 MB) / its

@@ -51,21 +51,9 @@ SIGNATURES = {
     "gpc_kmap_pairs_workspace_bytes": (c_sz, [c_i64, c_int]),
     "gpc_kmap_pairs_count": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gpc_kmap_pairs_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "gpc_spconv_pack_weights": (c_int, [c_vp, c_int, c_vp, c_vp]),
-    "gpc_spconv_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
-    "gpc_spconv_fwd_v3": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
-    "gpc_spconv_pack_weights_bf16": (c_int, [c_vp, c_int, c_vp, c_vp]),
-    "gpc_spconv_fwd_v4": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_spconv_pack_weights_frag": (c_int, [c_vp, c_int, c_vp, c_vp]),
-    "gpc_spconv_fwd_v5": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_spconv_fwd_v6": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     "gpc_spconv_fwd_v6_rows": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp]),
-    "gpc_kmap_rt8_workspace_bytes": (c_sz, [c_i64]),
-    "gpc_kmap_rt8_count": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "gpc_kmap_rt8_fill": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
-    "gpc_spconv_fwd_v7": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp]),
-    "gpc_spconv_fwd_v8": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
-    "gpc_spconv_pack_weights_umma": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "gpc_kmap_sparse_segments": (c_i64, [c_i64]),
     "gpc_kmap_sparse_workspace_bytes": (c_sz, [c_i64]),
     "gpc_kmap_sparse_count": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
@@ -74,15 +62,15 @@ SIGNATURES = {
     "gpc_spconv_sparse_fwd_rows": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_i64, c_vp]),
     "gpc_rows_split": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "gpc_rows_join": (c_int, [c_vp, c_i64, c_vp, c_vp]),
-    "gpc_spconv_fwd_tc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
-    "gpc_debug_conv_tc_profile": (c_int, [c_vp, c_int]),
     "gpc_debug_conv_um_profile": (c_int, [c_vp, c_int]),
-    "gpc_kmap_row_offsets": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "gpc_kmap_um_workspace_bytes": (c_sz, [c_i64, c_int]),
+    "gpc_kmap_um_count": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_kmap_um_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gpc_spconv_pack_weights_um": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "gpc_spconv_fwd_um": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
-    "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
-    "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp]),
+    "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gpc_head_cdf": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "gpc_head_cdf_sym": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gpc_split_symbol": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),

@@ -40,20 +40,16 @@ def _ptr(t: Optional[torch.Tensor]):
 
 @dataclass
 class KMap:
-    seg: torch.Tensor
-    pair_nbr: torch.Tensor
-    pair_row: torch.Tensor
-    pairs: Optional[torch.Tensor]
-    n_pairs: int
+    """Kernel map of one coordinate set (built once, shared by every conv on the set), in the form its conv kernel consumes."""
+    seg: torch.Tensor                         # first stream entry of every (tile, offset) segment
+    pairs: Optional[torch.Tensor]             # mma.sync / sparse conv: combined stream nbr | row << 32 | k << 48
+    n_pairs: int                              # stream entries (padded)
     tile_rows: int
-    hdr: Optional[torch.Tensor] = None        # rt8 format (conv variants >= 50)
-    toff: Optional[torch.Tensor] = None
-    tiles: Optional[torch.Tensor] = None
-    n_tiles: int = 0
-    n_real: int = 0                           # true (row, neighbour) pairs -- filled in bench profiling mode only
-    cta_rows: int = 0                         # > 0: tcgen05 conv; tile_rows == cta_rows / 4 (the quarters of a CTA tile)
-    _fill: object = None
-    v6_variant: int = 42                      # mma.sync conv: 42 = one warp per tile, 45 / 46 / 47 = offsets split over 2 / 8 / 16 warps
+    n_real: int = 0                           # true (row, neighbour) pairs
+    v6_variant: int = 42                      # mma.sync conv: 42 one warp per tile, 46 / 47 offsets split over 8 / 16 warps, 48 = v6d
+    um_rows: int = 0                          # > 0: tcgen05 conv (spconv_um.cu) with tiles of um_rows output rows; activations are split rows
+    pair_nbr: Optional[torch.Tensor] = None   # um: input row of every stream entry (0xFFFFFFFF = padding)
+    pair_off: Optional[torch.Tensor] = None   # um: byte offset of every entry's accumulator row
     sparse: bool = False                      # sparse big level: centre product + offset-sorted stragglers (spconv_sparse.cu)
     rowptr: Optional[torch.Tensor] = None     # sparse: first contribution of every row
     contrib: Optional[torch.Tensor] = None    # sparse: scratch [stragglers, 32] fp32, rewritten by every conv on the level
@@ -78,19 +74,12 @@ class DeviceWeights:
         self.prior_emb = f("prior_embedding.weight")
         self.target_emb = f("target_embedding.target_res_embedding.weight")
         self.convs = torch.stack([f(k) for k in W.CONV_KEYS]).contiguous()           # [18,125,32,32]
-        self.convs_packed = torch.empty_like(self.convs)                             # [18,125,16,32,2] for the FFMA2 kernels
         lib = _lib.load()
-        _lib.check(lib.gpc_spconv_pack_weights(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_packed),
-                                               C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights")
-        self.convs_frag = torch.empty_like(self.convs)                               # [18,125,2,2,2,32] uint4: mma A fragments of W^T
-        _lib.check(lib.gpc_spconv_pack_weights_frag(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_frag),
-                                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_frag")
-        self.convs_umma = torch.empty_like(self.convs)                               # [18,125,2,2 KB]: UMMA canonical images of W[k] hi / lo
-        _lib.check(lib.gpc_spconv_pack_weights_umma(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_umma),
-                                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_umma")
-        self.convs_bf16 = torch.empty_like(self.convs)                               # [18,125,2,8,32] x (4 x bf16): hi / lo halves
-        _lib.check(lib.gpc_spconv_pack_weights_bf16(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_bf16),
-                                                    C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), "gpc_spconv_pack_weights_bf16")
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        self.convs_frag = torch.empty_like(self.convs)       # [18,125,2,2,2,32] uint4: mma.sync A fragments of W^T (bf16 hi / lo)
+        _lib.check(lib.gpc_spconv_pack_weights_frag(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_frag), st), "gpc_spconv_pack_weights_frag")
+        self.convs_um = torch.empty_like(self.convs)         # [18,125,8,32,16 B]: tcgen05 A operand (W^T bf16 hi | lo), one TMEM lane per channel
+        _lib.check(lib.gpc_spconv_pack_weights_um(_ptr(self.convs), len(W.CONV_KEYS), _ptr(self.convs_um), st), "gpc_spconv_pack_weights_um")
         self.stage_emb = [None] + [f(f"pred_head_s{i}_emb.weight") for i in (1, 2, 3)]
         self.head = [tuple(f(f"pred_head_s{i}.{j}.{p}") for j, p in ((0, "weight"), (0, "bias"), (2, "weight"), (2, "bias")))
                      for i in range(4)]
@@ -104,24 +93,20 @@ class GausPcgcCodec:
         self.lib = _lib.load()
         self.dev = torch.device(device if device is not None else "cuda")
         self.w = weights
-        # 42 (default): the mma.sync conv (v6) on every level, tile shape by level size (_v6_config)
-        # 100: tcgen05 conv (spconv_tc.cu) on the big dense levels, v6 elsewhere; 101: same with the role profile.  Parity-green and
-        #      at par with v6 on the dense levels, but not faster end to end yet (profiles/r01_conv_tcgen05.md), hence opt-in
-        # other values < 70: one of the earlier kernels on every level (kept for A/B, tools/conv_ab.py)
-        self.conv_variant = int(os.environ.get("GPC_CONV_VARIANT", 42))
-        self.adaptive_tiles = os.environ.get("GPC_ADAPTIVE_TILES", "1") != "0" and tile_rows is None
-        self.tile_rows = int(tile_rows or os.environ.get("GPC_TILE_ROWS", 64 if self.conv_variant >= 30 else (128 if self.conv_variant >= 20 else 256)))
-        # a level runs the tcgen05 conv when it has enough rows to fill 148 one-per-SM CTAs a few times over AND enough pairs per
-        # row for the 128-row MMA chunks of one offset to be reasonably full (tools/conv_ab.py: break-even near 5 pairs per row)
-        self.tc_min_rows = int(os.environ.get("GPC_TC_MIN_ROWS", 150_000))
-        self.tc_min_density = float(os.environ.get("GPC_TC_MIN_DENSITY", 5.0))
-        self.tc_cta_rows = int(os.environ.get("GPC_TC_CTA_ROWS", 1024))
-        # big levels with fewer pairs per row than this run the centre + stragglers conv (spconv_sparse.cu); 0 disables it.
-        # Density only falls from one octree level to the next finer one, so after the first sparse level the finer ones skip
-        # the tiled count (both encoder and decoder walk the levels coarse -> fine and take the same decisions).
-        self.sparse_max_density = float(os.environ.get("GPC_SPARSE_MAX_DENSITY", 4.5))
-        self.sparse_min_rows = int(os.environ.get("GPC_SPARSE_MIN_ROWS", 150_000))
-        self._seen_sparse = False
+        # Which conv kernel a level runs is a function of the LEVEL ONLY (rows, pairs per row): encoder and decoder must take the
+        # same decision, because each kernel has its own fp32 summation order and the range coder needs bit-identical CDFs on both
+        # sides.  The thresholds are therefore constants of the bitstream format, not tunables; tools/ and tests/ may override the
+        # attributes on a codec object they use for BOTH directions (A/B timing, kernel-family parity).
+        #   rows >= UM_MIN_ROWS and >= SPARSE_MAX_DENSITY pairs per row: tcgen05 conv (spconv_um.cu), split-row activations
+        #   rows >= SPARSE_MIN_ROWS and  < SPARSE_MAX_DENSITY pairs per row: centre product + sorted stragglers (spconv_sparse.cu)
+        #   otherwise: the mma.sync conv, tile shape by level size (_v6_config)
+        self.um_min_rows = 150_000
+        self.sparse_max_density = 4.5
+        self.sparse_min_rows = 150_000
+        self.adaptive_tiles = tile_rows is None       # tests: a fixed tile height / kernel variant of the mma.sync conv on every level
+        self.tile_rows = int(tile_rows or 64)
+        self.v6_variant = 42
+        self.um_tile_rows = 512                       # output rows per CTA of the tcgen05 conv (256 / 384 / 512 / 1024 are built)
         self._fns: Dict[str, object] = {}
         self._stream_h = None
         n_thr = ac_threads or int(os.environ.get("GPC_AC_THREADS", min(16, len(os.sched_getaffinity(0)))))
@@ -130,16 +115,18 @@ class GausPcgcCodec:
         self._pinned_dec: Optional[torch.Tensor] = None
         # decoder wavefront (stages of a level overlap chunk by chunk): levels with >= wave_min_rows rows, chunks of wave_chunk_rows
         # rows (a multiple of 8192 = the sparse conv's row blocks and of the v6d tile heights)
-        self.wave_decode = os.environ.get("GPC_WAVE_DECODE", "1") != "0"
-        self.wave_min_rows = int(os.environ.get("GPC_WAVE_MIN_ROWS", 150_000))
-        self.wave_chunk_rows = int(os.environ.get("GPC_WAVE_CHUNK_ROWS", 32768))
-        self.wave_plane_lag = os.environ.get("GPC_WAVE_PLANE_LAG", "1") != "0"   # stage i+1 trails stage i by planes, not by two chunks
-        self.wave_streams = os.environ.get("GPC_WAVE_STREAMS", "1") != "0"
+        # (how the decoder ORDERS its work -- wavefront or stage by stage -- does not change a single bit of any CDF: the row-range
+        # launches compute the same sums; tests/test_gpu_parity.py::test_decoder_wavefront)
+        self.wave_decode = True
+        self.wave_min_rows = 150_000
+        self.wave_chunk_rows = 32768
+        self.wave_plane_lag = True                    # stage i+1 trails stage i by planes, not by two chunks
+        self.wave_streams = True
         self._wave_side: Optional[list] = None
         self._wave_buf: Optional[torch.Tensor] = None
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
-        self.wave_first_rows = int(os.environ.get("GPC_WAVE_FIRST_ROWS", 8192))        # size / number of the small leading chunks
-        self.wave_first_chunks = int(os.environ.get("GPC_WAVE_FIRST_CHUNKS", 0))     # measured: small leading chunks cost more than they save (dec 0.242 vs 0.218 s)
+        self.wave_first_rows = 8192                   # size / number of the small leading chunks
+        self.wave_first_chunks = 0                    # measured: small leading chunks cost more than they save (dec 0.242 vs 0.218 s)
         self._launch_base = 0
         self.last_stats: Dict[str, float] = {}
         self._segments: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
@@ -296,14 +283,12 @@ class GausPcgcCodec:
 
     # ------------------------------------------------------------------ kernel map / conv
     def _v6_config(self, n: int) -> Tuple[int, int]:
-        """(rows per CTA, kernel variant) of the mma.sync conv for a level of n rows (tools/conv_ab.py, AB_MIN_ROWS=50):
-        64 rows per warp on big levels (W^T reuse); fewer rows on the coarse levels so that they still fill the 148 SMs; on the
-        coarse levels the 125 offsets of a tile are additionally split over 4 / 8 / 16 warps (variants 44 / 46 / 47): those
+        """(rows per CTA, kernel variant) of the mma.sync conv for a level of n rows (tools/conv_ab.py):
+        128 / 64 rows per warp on big levels (W^T reuse, v6d); fewer rows on the coarse levels so that they still fill the 148 SMs;
+        on the coarse levels the 125 offsets of a tile are additionally split over 8 / 16 warps (variants 46 / 47): those
         launches are bound by one warp's chain of dependent 8-pair tiles, ~63 us each before, 15-30 us now."""
-        if self.conv_variant < 100 and (self.conv_variant != 42 or not self.adaptive_tiles):
-            return self.tile_rows, self.conv_variant
         if not self.adaptive_tiles:
-            return 64, 42
+            return self.tile_rows, self.v6_variant
         if n >= 150_000:
             return 128, 48          # v6d: rows straight into the MMA fragments, 128-row tiles halve the W^T traffic per pair
         if n >= 40_000:
@@ -314,7 +299,8 @@ class GausPcgcCodec:
             return 16, 46
         return 8, 47
 
-    def _pair_stream(self, dense: torch.Tensor, n: int, tr: int, pad: int, split: bool) -> KMap:
+    def _count_pairs(self, dense: torch.Tensor, n: int, tr: int, pad: int):
+        """first pass over the dense map: seg (exclusive scan of the padded per-(tile, offset) counts), entries, true pairs"""
         tiles = (n + tr - 1) // tr
         seg = self._empty((tiles * 126 + 1,), torch.int32)
         cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
@@ -322,14 +308,32 @@ class GausPcgcCodec:
         ws = self._ws(ws_b)
         self._call("gpc_kmap_pairs_count", _ptr(dense), n, tr, pad, _ptr(seg), _ptr(cnt), _ptr(ws), ws_b, self._stream())
         n_pairs, n_real = (int(v) for v in cnt.tolist())
-        pair_nbr = self._empty((max(n_pairs, 1),), torch.int32) if split else None
-        pair_row = self._empty((max(n_pairs, 1),), torch.int16) if split else None
-        pairs = self._empty((max(n_pairs, 1),), torch.int64) if self.conv_variant >= 10 else None
-        km = KMap(seg, pair_nbr, pair_row, pairs, n_pairs, tr)
-        km.n_real = n_real
-        km._fill = lambda: self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(pair_nbr), _ptr(pair_row), _ptr(pairs),
-                                      n_pairs if pad > 1 else 0, self._stream())
-        return km
+        return seg, n_pairs, n_real
+
+    def _v6_map(self, dense: torch.Tensor, n: int, tr: int, v6v: int, counted=None) -> KMap:
+        seg, n_pairs, n_real = counted if counted is not None else self._count_pairs(dense, n, tr, 8)
+        pairs = self._empty((max(n_pairs, 1),), torch.int64)
+        self._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg), None, None, _ptr(pairs), n_pairs, self._stream())
+        return KMap(seg, pairs, n_pairs, tr, n_real=n_real, v6_variant=v6v)
+
+    def _count_um(self, dense: torch.Tensor, n: int, tr: int):
+        """the tcgen05 conv's tiling of the level: seg, stream entries (padded to 16 per (tile, offset)), true pairs"""
+        tiles = (n + tr - 1) // tr
+        seg = self._empty((tiles * 126 + 1,), torch.int32)
+        tot = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        ws_b = self.lib.gpc_kmap_um_workspace_bytes(n, tr)
+        ws = self._ws(ws_b)
+        self._call("gpc_kmap_um_count", _ptr(dense), n, tr, _ptr(seg), _ptr(tot), _ptr(ws), ws_b, self._stream())
+        n_pairs, n_real = (int(v) for v in tot.tolist())
+        return seg, n_pairs, n_real
+
+    def _um_map(self, dense: torch.Tensor, n: int, tr: int, counted=None) -> KMap:
+        """pair stream of the tcgen05 conv: tiles of tr rows, segments padded to 16 entries, input rows + accumulator-row offsets"""
+        seg, n_pairs, n_real = counted if counted is not None else self._count_um(dense, n, tr)
+        nbr = self._empty((max(n_pairs, 1),), torch.int32)
+        off = self._empty((max(n_pairs, 1),), torch.int32)
+        self._call("gpc_kmap_um_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(nbr), _ptr(off), self._stream())
+        return KMap(seg, None, n_pairs, tr, n_real=n_real, um_rows=tr, pair_nbr=nbr, pair_off=off)
 
     def _sparse_map(self, dense: torch.Tensor, n: int) -> KMap:
         m = int(self.lib.gpc_kmap_sparse_segments(n))
@@ -342,56 +346,43 @@ class GausPcgcCodec:
         n_entries, n_strag = (int(v) for v in tot.tolist())
         pairs = self._empty((max(n_entries, 1),), torch.int64)
         self._call("gpc_kmap_sparse_fill", _ptr(dense), n, _ptr(seg), _ptr(rowptr), _ptr(ws), _ptr(pairs), n_entries, self._stream())
-        km = KMap(seg, None, None, pairs, n_entries, 0)
-        km.n_real = n + n_strag
-        km.sparse, km.rowptr = True, rowptr
+        km = KMap(seg, pairs, n_entries, 0, n_real=n + n_strag, sparse=True, rowptr=rowptr)
         km.contrib = self._empty((max(n_strag, 1), 32), torch.float32)
         return km
 
-    def build_kmap(self, keys: torch.Tensor, keep_dense: bool = False):
+    def dense_map(self, keys: torch.Tensor) -> torch.Tensor:
+        """hash table of the level + the offset-major [125][n] map of input rows (-1 = absent)"""
         n = keys.shape[0]
         cap = self.lib.gpc_hash_capacity(n)
         table = self._ws(cap * 16)
         self._call("gpc_hash_build", _ptr(keys), n, _ptr(table), cap, self._stream())
         dense = self._empty((W.reference_layout()["prior_resnet.0.kernel"][0], n), torch.int32)
         self._call("gpc_kmap_dense", _ptr(table), cap, _ptr(keys), n, _ptr(dense), self._stream())
-        if 50 <= self.conv_variant < 60 and not keep_dense:
-            nst = (n + 63) // 64
-            hdr = self._empty((nst * 128,), torch.uint8)
-            toff = self._empty((nst * 126 + 1,), torch.int32)
-            cnt = torch.zeros(2, dtype=torch.int32, device=self.dev)
-            ws_b = self.lib.gpc_kmap_rt8_workspace_bytes(n)
-            ws = self._ws(ws_b)
-            self._call("gpc_kmap_rt8_count", _ptr(dense), n, _ptr(hdr), _ptr(toff), _ptr(cnt), _ptr(ws), ws_b, self._stream())
-            if self.conv_profile is not None:
-                cnt[1] = (dense >= 0).sum()               # bench only: true pair count for the roofline arithmetic
-            c = cnt.tolist()
-            n_tiles = int(c[0])
-            tl = self._empty((max(n_tiles, 1) * 8,), torch.int32)
-            self._call("gpc_kmap_rt8_fill", _ptr(dense), n, _ptr(toff), _ptr(tl), self._stream())
-            return KMap(None, None, None, None, int(c[1]), 64, hdr, toff, tl, n_tiles, int(c[1]))
-        km = None
-        sparse_ok = (self.conv_variant in (42, 100) and self.sparse_max_density > 0 and not keep_dense
-                     and self.sparse_min_rows <= n < 30_000_000)         # 32-bit straggler indices: n * 124 < 2^32
-        if sparse_ok and self._seen_sparse:
-            return self._sparse_map(dense, n)
-        if self.conv_variant >= 100 and not keep_dense and n >= self.tc_min_rows:
-            km = self._pair_stream(dense, n, self.tc_cta_rows // 4, 1, False)        # quarters of a tcgen05 CTA tile
-            if km.n_real >= self.tc_min_density * n:
-                km.cta_rows = self.tc_cta_rows
-            else:
-                km = None                                                            # too sparse: count again with the warp tiling
-        if km is None:
-            pad = 8 if ((40 <= self.conv_variant < 70 or self.conv_variant >= 100) and not keep_dense) else 1
+        return dense
+
+    def build_kmap(self, keys: torch.Tensor, family: Optional[str] = None) -> KMap:
+        """Kernel map of a coordinate set in the form of the conv kernel the level runs.  The family is a function of the level only
+        (rows, pairs per row -- see __init__); `family` ("v6" | "um" | "sparse") forces one (tests / tools, both directions alike)."""
+        n = keys.shape[0]
+        dense = self.dense_map(keys)
+        big = n >= min(self.um_min_rows, self.sparse_min_rows)
+        if family is None and not big:
+            family = "v6"
+        if family == "v6":
             tr, v6v = self._v6_config(n)
-            km = self._pair_stream(dense, n, tr, pad, self.conv_variant < 10 or keep_dense)
-            km.v6_variant = v6v
-            if sparse_ok and km.n_real < self.sparse_max_density * n:
-                self._seen_sparse = True
-                return self._sparse_map(dense, n)
-        km._fill()
-        km._fill = None
-        return (km, dense) if keep_dense else km
+            return self._v6_map(dense, n, tr, v6v)
+        if family == "sparse":
+            return self._sparse_map(dense, n)
+        # big level: one count with the tcgen05 tiling tells the density (pairs per row, centre included)
+        counted = self._count_um(dense, n, self.um_tile_rows)
+        density = counted[2] / max(n, 1)
+        if family is None:
+            if n >= self.sparse_min_rows and 0 < self.sparse_max_density and density < self.sparse_max_density and n < 30_000_000:
+                return self._sparse_map(dense, n)            # 32-bit straggler indices: n * 124 < 2^32
+            if n < self.um_min_rows:
+                tr, v6v = self._v6_config(n)
+                return self._v6_map(dense, n, tr, v6v)
+        return self._um_map(dense, n, self.um_tile_rows, counted)
 
     def split_rows(self, x: torch.Tensor) -> torch.Tensor:
         """fp32 rows [n,32] -> split rows (int32 [n,32]: 16 words of bf16x2 hi | 16 words of bf16x2 lo)."""
@@ -401,63 +392,46 @@ class GausPcgcCodec:
 
     def conv(self, x: torch.Tensor, widx: int, km: KMap, residual: Optional[torch.Tensor] = None, relu: bool = False,
              out: Optional[torch.Tensor] = None, fmt: str = "f32", rows: Optional[Tuple[int, int]] = None):
-        """One sparse conv.  Activations are fp32 rows (float32 tensors) or split rows (int32 tensors, tcgen05 levels
-        only); fmt = "f32" | "split" | "both" selects what is written ("both" returns (f32, split)).
-        rows = (r0, r1): only the output rows [r0, r1) of `out` are computed (decoder wavefront; v6d and sparse levels)."""
+        """One sparse conv.  Activations are fp32 rows (float32 tensors) or split rows (int32 tensors: the tcgen05 levels);
+        fmt = "f32" | "split" | "both" selects what a tcgen05 level writes ("both" returns (f32, split)); out = the fp32 output
+        buffer, or for fmt == "split" the split output buffer.
+        rows = (r0, r1): only the output rows [r0, r1) are computed (whole tiles / blocks; decoder wavefront)."""
         n = x.shape[0]
-        if rows is not None:
-            assert out is not None and fmt == "f32" and x.dtype == torch.float32 and not km.cta_rows
-            if km.sparse:
-                self._call("gpc_spconv_sparse_fwd_rows", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs),
-                           _ptr(km.rowptr), n, km.n_pairs, _ptr(km.contrib), _ptr(residual), 1 if relu else 0, _ptr(out),
-                           rows[0], rows[1], self._stream())
-            else:
-                self._call("gpc_spconv_fwd_v6_rows", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n,
-                           km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(out), km.v6_variant, rows[0], rows[1], self._stream())
-            return out
-        if km.cta_rows:
+        r0, r1 = rows if rows is not None else (0, 0)
+        flags = 1 if relu else 0
+        if km.um_rows:
             xs = x if x.dtype == torch.int32 else self.split_rows(x)
-            y = (out if out is not None else self._empty((n, 32), torch.float32)) if fmt in ("f32", "both") else None
-            ys = self._empty((n, 32), torch.int32) if fmt in ("split", "both") else None
-            self._prof_conv_begin()
-            flags = (1 if relu else 0) | (2 if (residual is not None and residual.dtype == torch.int32) else 0)
-            self._call("gpc_spconv_fwd_tc", _ptr(xs), _ptr(self.w.convs_umma[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.cta_rows,
-                       _ptr(residual), flags, _ptr(y), _ptr(ys), 1 if self.conv_variant == 101 else 0, self._stream())
-            self._prof_conv_end(n, km)
+            y = ys = None
+            if fmt in ("f32", "both"):
+                y = out if (out is not None and fmt == "f32") else self._empty((n, 32), torch.float32)
+            if fmt in ("split", "both"):
+                ys = out if (out is not None and fmt == "split") else self._empty((n, 32), torch.int32)
+            if residual is not None and residual.dtype == torch.int32:
+                flags |= 2
+            if rows is None:
+                self._prof_conv_begin()
+            self._call("gpc_spconv_fwd_um", _ptr(xs), _ptr(self.w.convs_um[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_off), n,
+                       km.um_rows, _ptr(residual), flags, _ptr(y), _ptr(ys), r0, r1, self._stream())
+            if rows is None:
+                self._prof_conv_end(n, km)
             return y if fmt == "f32" else (ys if fmt == "split" else (y, ys))
         assert fmt == "f32" and x.dtype == torch.float32
         y = out if out is not None else self._empty((n, 32), torch.float32)
+        if rows is not None:
+            if km.sparse:
+                self._call("gpc_spconv_sparse_fwd_rows", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs),
+                           _ptr(km.rowptr), n, km.n_pairs, _ptr(km.contrib), _ptr(residual), flags, _ptr(y), r0, r1, self._stream())
+            else:
+                self._call("gpc_spconv_fwd_v6_rows", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n,
+                           km.tile_rows, _ptr(residual), flags, _ptr(y), km.v6_variant, r0, r1, self._stream())
+            return y
         self._prof_conv_begin()
         if km.sparse:
             self._call("gpc_spconv_sparse_fwd", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), _ptr(km.rowptr), n,
-                       km.n_pairs, _ptr(km.contrib), _ptr(residual), 1 if relu else 0, _ptr(y), self._stream())
-            self._prof_conv_end(n, km)
-            return y
-        wt = self.w.convs[widx] if self.conv_variant == 0 else self.w.convs_packed[widx]
-        if self.conv_variant >= 100 or self.conv_variant == 42:
-            self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), km.v6_variant, self._stream())
-        elif self.conv_variant >= 60:
-            self._call("gpc_spconv_fwd_v8", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
-        elif self.conv_variant >= 50:
-            self._call("gpc_spconv_fwd_v7", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.toff), _ptr(km.hdr), _ptr(km.tiles), n,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
-        elif self.conv_variant >= 40:
-            self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
-        elif self.conv_variant >= 30:
-            self._call("gpc_spconv_fwd_v5", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
-        elif self.conv_variant >= 20:
-            self._call("gpc_spconv_fwd_v4", _ptr(x), _ptr(self.w.convs_bf16[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
-                       _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
-        elif self.conv_variant >= 10:
-            self._call("gpc_spconv_fwd_v3", _ptr(x), _ptr(wt), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows, _ptr(residual),
-                       1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+                       km.n_pairs, _ptr(km.contrib), _ptr(residual), flags, _ptr(y), self._stream())
         else:
-            self._call("gpc_spconv_fwd", _ptr(x), _ptr(wt), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_row), n,
-                       km.tile_rows, _ptr(residual), 1 if relu else 0, _ptr(y), self.conv_variant, self._stream())
+            self._call("gpc_spconv_fwd_v6", _ptr(x), _ptr(self.w.convs_frag[widx]), _ptr(km.seg), _ptr(km.pairs), n, km.tile_rows,
+                       _ptr(residual), flags, _ptr(y), km.v6_variant, self._stream())
         self._prof_conv_end(n, km)
         return y
 
@@ -501,7 +475,7 @@ class GausPcgcCodec:
             self._prof_close(grp)
 
     def _res_stack(self, x: torch.Tensor, ids, km: KMap, final: str):
-        if km.cta_rows:            # tcgen05 level: everything between the first and the last conv stays in split rows
+        if km.um_rows:             # tcgen05 level: everything between the first and the last conv stays in split rows
             x = self.conv(x, ids[0], km, relu=True, fmt="split")
             t = self.conv(x, ids[1], km, relu=True, fmt="split")
             x = self.conv(t, ids[2], km, residual=x, relu=True, fmt="split")
@@ -515,19 +489,23 @@ class GausPcgcCodec:
 
     def level_features(self, parent: Level, n_child: int, child_kmap: Optional[KMap] = None):
         """pcc_utils.py:99-109 == :300-311: prior stack on S_d, expand, target embedding, target stack.
-        child_kmap: the kernel map of the child set if the caller has built it already (encoder)."""
+        child_kmap: the kernel map of the child set if the caller has built it already (encoder).
+        Returns (child level, u): u = fp32 rows, or (fp32 rows, split rows) on a tcgen05 level."""
         if parent.kmap is None:
             parent.kmap = self.build_kmap(parent.keys)
-        f = self._empty((parent.n, 32), torch.float32)
-        self._call("gpc_embed_rows", _ptr(parent.occ), parent.n, _ptr(self.w.prior_emb), _ptr(f), self._stream())
-        f = self.res_stack(f, W.PRIOR_CONVS, parent.kmap)
-        ck, cp = self.expand(parent, n_child)
-        u0 = self._empty((n_child, 32), torch.float32)
-        self._call("gpc_gather_parent_add_octant", _ptr(f), _ptr(cp), _ptr(ck), n_child, _ptr(self.w.target_emb), _ptr(u0),
+        pum = bool(parent.kmap.um_rows)
+        f = self._empty((parent.n, 32), torch.int32 if pum else torch.float32)
+        self._call("gpc_embed_rows", _ptr(parent.occ), parent.n, _ptr(self.w.prior_emb), None if pum else _ptr(f), _ptr(f) if pum else None,
                    self._stream())
+        f = self.res_stack(f, W.PRIOR_CONVS, parent.kmap)            # fp32 rows (the children gather them)
+        ck, cp = self.expand(parent, n_child)
         child = Level(ck, None, n_child, child_kmap if child_kmap is not None else self.build_kmap(ck))
+        cum = bool(child.kmap.um_rows)
+        u0 = self._empty((n_child, 32), torch.int32 if cum else torch.float32)
+        self._call("gpc_gather_parent_add_octant", _ptr(f), _ptr(cp), _ptr(ck), n_child, _ptr(self.w.target_emb), None if cum else _ptr(u0),
+                   _ptr(u0) if cum else None, self._stream())
         # tcgen05 level: u is needed as fp32 rows (context embeddings) and as split rows (stage 0 conv input)
-        u = self.res_stack(u0, W.TARGET_CONVS, child.kmap, final="both" if child.kmap.cta_rows else "f32")
+        u = self.res_stack(u0, W.TARGET_CONVS, child.kmap, final="both" if cum else "f32")
         return child, u
 
     def stage_cdf(self, u: torch.Tensor, occ_partial: Optional[torch.Tensor], i: int, km: KMap, cdf_out: Optional[torch.Tensor],
@@ -537,15 +515,16 @@ class GausPcgcCodec:
         and only (c_low, c_high) of that symbol is written (4 B per row for the host coder)."""
         u, u_split = u if isinstance(u, tuple) else (u, None)
         n = u.shape[0]
+        um = bool(km.um_rows)
         if i == 0:
-            f = u_split if u_split is not None else u
+            f = u_split if um else u
         else:
-            f = self._empty((n, 32), torch.float32)
-            self._call("gpc_add_ctx_embed", _ptr(u), _ptr(occ_partial), CTX_SHIFT[i], _ptr(self.w.stage_emb[i]), n, _ptr(f),
-                       self._stream())
+            f = self._empty((n, 32), torch.int32 if um else torch.float32)
+            self._call("gpc_add_ctx_embed", _ptr(u), _ptr(occ_partial), CTX_SHIFT[i], _ptr(self.w.stage_emb[i]), n, None if um else _ptr(f),
+                       _ptr(f) if um else None, self._stream())
         c0, c1 = W.stage_convs(i)
         grp = self._prof_open()
-        t = self.conv(f, c0, km, relu=True, fmt="split" if km.cta_rows else "f32")
+        t = self.conv(f, c0, km, relu=True, fmt="split" if um else "f32")
         t = self.conv(t, c1, km)
         self._prof_close(grp)
         w1, b1, w2, b2 = self.w.head[i]
@@ -592,7 +571,6 @@ class GausPcgcCodec:
         """
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
-        self._seen_sparse = False
         self._stream_h = torch.cuda.current_stream(self.dev).cuda_stream
         self._seg_begin()
         xyz = xyz.contiguous()
@@ -678,9 +656,9 @@ class GausPcgcCodec:
     # 0.35 s decode at 1M anchors) overlaps with itself.
     def _wave_ok(self, child: Level, n: int) -> bool:
         km = child.kmap
-        if not self.wave_decode or n < self.wave_min_rows or km.cta_rows:
+        if not self.wave_decode or n < self.wave_min_rows:
             return False
-        if not (km.sparse or (getattr(km, "v6_variant", 0) == 48 and self.wave_chunk_rows % km.tile_rows == 0
+        if not (km.sparse or ((km.um_rows or km.v6_variant == 48) and self.wave_chunk_rows % km.tile_rows == 0
                               and self.wave_first_rows % km.tile_rows == 0)):
             return False
         if km.sparse and (self.wave_chunk_rows % 8192 or self.wave_first_rows % 8192):
@@ -740,7 +718,8 @@ class GausPcgcCodec:
         km = child.kmap
         chunks = self._wave_chunks(n)
         nc = len(chunks)
-        u = u[0] if isinstance(u, tuple) else u
+        u, u_split = u if isinstance(u, tuple) else (u, None)
+        um = bool(km.um_rows)                  # tcgen05 level: conv inputs (context-embedded rows, first-conv outputs) are split rows
         Lps = [a + 1 for a in W.STAGE_ALPHABETS]
         # pinned staging: the four stages' CDF rows and symbols live at the same time
         need = n * (2 * sum(Lps) + 4) + 4096
@@ -762,9 +741,11 @@ class GausPcgcCodec:
             self._wave_buf = None
             self._wave_buf = torch.empty(int(11 * n * 32 * 1.3) + 1024, dtype=torch.float32, device=self.dev)
         carve = [self._wave_buf[k * n * 32:(k + 1) * n * 32].view(n, 32) for k in range(11)]
-        f = [None] + carve[0:3]
-        t0 = carve[3:7]
+        as_in = (lambda t: t.view(torch.int32)) if um else (lambda t: t)
+        f = [None] + [as_in(t) for t in carve[0:3]]
+        t0 = [as_in(t) for t in carve[3:7]]
         t1 = carve[7:11]
+        cfmt = "split" if um else "f32"
         stream = torch.cuda.current_stream(self.dev)
         ev_q = [queue.Queue() for _ in range(4)]
         done_q: "queue.Queue" = queue.Queue()
@@ -835,7 +816,7 @@ class GausPcgcCodec:
         try:
             # stage 0 needs no symbols: whole level at once, CDFs handed over chunk by chunk
             c0, c1 = W.stage_convs(0)
-            self.conv(u, c0, km, relu=True, out=t0[0])
+            self.conv(u_split if um else u, c0, km, relu=True, out=t0[0], fmt=cfmt)
             self.conv(t0[0], c1, km, out=t1[0])
             for c in range(nc):
                 emit_cdf(0, c)
@@ -863,10 +844,11 @@ class GausPcgcCodec:
                         continue
                     k0, k1 = W.stage_convs(j)
                     if r1 > r0:
-                        call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0, p_f[j] + r0 * 128, sh)
+                        call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0,
+                             None if um else p_f[j] + r0 * 128, p_f[j] + r0 * 128 if um else None, sh)
                     a0, a1 = (CA[j][c - 1] if c else 0), CA[j][c]
                     if a1 > a0:
-                        self.conv(f[j], k0, km, relu=True, out=t0[j], rows=(a0, a1))
+                        self.conv(f[j], k0, km, relu=True, out=t0[j], rows=(a0, a1), fmt=cfmt)
                     q0, q1 = P[j][c]
                     if q1 > q0:
                         self.conv(t0[j], k1, km, out=t1[j], rows=(q0, q1))
@@ -878,10 +860,11 @@ class GausPcgcCodec:
                 if i == 3:
                     continue
                 k0, k1 = W.stage_convs(j)
-                call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0, p_f[j] + r0 * 128, sh)
+                call("gpc_add_ctx_embed", p_u + r0 * 128, p_occ + r0, CTX_SHIFT[j], embs[j], r1 - r0,
+                     None if um else p_f[j] + r0 * 128, p_f[j] + r0 * 128 if um else None, sh)
                 last = c == nc - 1
                 for cc in ([c - 1] if c >= 1 else []) + ([c] if last else []):          # first conv: inputs of chunks cc-1 .. cc+1 are there
-                    self.conv(f[j], k0, km, relu=True, out=t0[j], rows=chunks[cc])
+                    self.conv(f[j], k0, km, relu=True, out=t0[j], rows=chunks[cc], fmt=cfmt)
                 for cc in ([c - 2] if c >= 2 else []) + ([c - 1, c] if last else []):
                     if cc < 0:
                         continue
@@ -918,7 +901,6 @@ class GausPcgcCodec:
         """
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
-        self._seen_sparse = False
         self._stream_h = torch.cuda.current_stream(self.dev).cuda_stream
         if len(streams) % 4:
             raise ValueError("stream count must be a multiple of 4 (one group per octree level)")

@@ -8,55 +8,68 @@
 #include "common.cuh"
 
 // ---------------------------------------------------------------- embeddings (float4 lanes: 8 threads per 128 B row)
-__global__ void embed_rows_kernel(const u8 *__restrict__ idx, i64 n, const float4 *__restrict__ table, float4 *__restrict__ out) {
+// Every producer of conv inputs can write fp32 rows, split rows (32 x bf16 hi | 32 x bf16 lo, the operand format of the tcgen05 conv,
+// spconv_um.cu) or both: channels 4c .. 4c + 3 of a row are hi words 2c, 2c + 1 and lo words 16 + 2c, 17 + 2c.
+__device__ __forceinline__ void store_quad(float4 *out, u32 *out_split, i64 row, int c, float4 v) {
+    if (out) out[row * 8 + c] = v;
+    if (out_split) {
+        u32 h0, l0, h1, l1;
+        split_bf16(v.x, v.y, h0, l0);
+        split_bf16(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2 *>(out_split + row * 32 + 2 * c) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2 *>(out_split + row * 32 + 16 + 2 * c) = make_uint2(l0, l1);
+    }
+}
+__global__ void embed_rows_kernel(const u8 *__restrict__ idx, i64 n, const float4 *__restrict__ table, float4 *__restrict__ out,
+                                  u32 *__restrict__ out_split) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 o = g >> 3;
     if (o >= n) return;
     const int c = (int)(g & 7);
-    out[o * 8 + c] = __ldg(table + (i64)idx[o] * 8 + c);
+    store_quad(out, out_split, o, c, __ldg(table + (i64)idx[o] * 8 + c));
 }
-extern "C" int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *stream) {
+extern "C" int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *out_split, void *stream) {
     if (n <= 0) return GPC_OK;
-    embed_rows_kernel<<<cdiv(n * 8, 256), 256, 0, as_stream(stream)>>>(idx, n, (const float4 *)table, (float4 *)out);
+    embed_rows_kernel<<<cdiv(n * 8, 256), 256, 0, as_stream(stream)>>>(idx, n, (const float4 *)table, (float4 *)out, (u32 *)out_split);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
 
 __global__ void gather_parent_add_octant_kernel(const float4 *__restrict__ feat, const u32 *__restrict__ parent,
                                                 const u64 *__restrict__ child_keys, i64 n, const float4 *__restrict__ temb,
-                                                float4 *__restrict__ out) {
+                                                float4 *__restrict__ out, u32 *__restrict__ out_split) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 j = g >> 3;
     if (j >= n) return;
     const int c = (int)(g & 7);
     const float4 a = __ldg(feat + (i64)parent[j] * 8 + c);
     const float4 e = __ldg(temb + (i64)key_octant(child_keys[j]) * 8 + c);
-    out[j * 8 + c] = make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
+    store_quad(out, out_split, j, c, make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w));
 }
 extern "C" int gpc_gather_parent_add_octant(const float *feat, const uint32_t *parent, const uint64_t *child_keys,
-                                            int64_t n_child, const float *temb, float *out, void *stream) {
+                                            int64_t n_child, const float *temb, float *out, void *out_split, void *stream) {
     if (n_child <= 0) return GPC_OK;
     gather_parent_add_octant_kernel<<<cdiv(n_child * 8, 256), 256, 0, as_stream(stream)>>>(
-        (const float4 *)feat, parent, child_keys, n_child, (const float4 *)temb, (float4 *)out);
+        (const float4 *)feat, parent, child_keys, n_child, (const float4 *)temb, (float4 *)out, (u32 *)out_split);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
 
 __global__ void add_ctx_embed_kernel(const float4 *__restrict__ u, const u8 *__restrict__ occ, int shift,
-                                     const float4 *__restrict__ emb, i64 n, float4 *__restrict__ out) {
+                                     const float4 *__restrict__ emb, i64 n, float4 *__restrict__ out, u32 *__restrict__ out_split) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     i64 o = g >> 3;
     if (o >= n) return;
     const int c = (int)(g & 7);
     const float4 a = u[o * 8 + c];
     const float4 e = __ldg(emb + (i64)(occ[o] >> shift) * 8 + c);
-    out[o * 8 + c] = make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
+    store_quad(out, out_split, o, c, make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w));
 }
 extern "C" int gpc_add_ctx_embed(const float *u, const uint8_t *occ, int shift, const float *emb, int64_t n, float *out,
-                                 void *stream) {
+                                 void *out_split, void *stream) {
     if (n <= 0) return GPC_OK;
     add_ctx_embed_kernel<<<cdiv(n * 8, 256), 256, 0, as_stream(stream)>>>((const float4 *)u, occ, shift, (const float4 *)emb, n,
-                                                                          (float4 *)out);
+                                                                          (float4 *)out, (u32 *)out_split);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }

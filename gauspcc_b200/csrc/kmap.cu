@@ -328,83 +328,90 @@ extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows,
 }
 
 
-// ---------------------------------------------------------------- row-tied 8-row tiles ("rt8") for spconv v7
-// Sub-tile = 64 consecutive output rows = 8 groups of 8 rows.  For every (sub-tile, offset k) the header byte
-// says which groups have at least one neighbour at k; every such group gets one 8-entry tile: entry g = input
-// row of (output row 8j+g) + d_k, or 0xFFFFFFFF.  Tiles of a sub-tile are stored in (k, group) order;
-// toff[st*126 + k] = index of the first tile of (st, k) (exclusive scan, toff[st*126+125] = next sub-tile).
-constexpr int RT_TW = 64;
-
-__device__ __forceinline__ u32 rt8_mask(const i32 *__restrict__ map, i64 n, i64 r0, int k, int lane, i32 &v0, i32 &v1) {
-    const i64 ra = r0 + lane, rb = r0 + 32 + lane;
-    v0 = ra < n ? map[(i64)k * n + ra] : -1;
-    v1 = rb < n ? map[(i64)k * n + rb] : -1;
-    const u32 b0 = __ballot_sync(0xFFFFFFFFu, v0 >= 0), b1 = __ballot_sync(0xFFFFFFFFu, v1 >= 0);
-    u32 m = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if ((b0 >> (8 * j)) & 0xFFu) m |= 1u << j;
-        if ((b1 >> (8 * j)) & 0xFFu) m |= 1u << (4 + j);
+// ---------------------------------------------------------------- pair stream of the tcgen05 conv (spconv_um.cu)
+// Tiles of 256 .. 1024 output rows; one WARP per (tile, offset) cell: the cell's slice of the offset-major dense map is tile_rows
+// consecutive ints, read with coalesced loads and ranked with ballots (the block-per-tile kernels above walk the 125 offsets one
+// after the other with three block barriers each).  Every non-empty cell is padded to a multiple of 16 entries; the stream holds,
+// per entry, the input row (padding: 0xFFFFFFFF = out of bounds for the gather) and the BYTE OFFSET of the pair's accumulator row
+// inside the tile (row * 128; padding: the dummy row tile_rows * 128).
+__global__ void __launch_bounds__(128) kmap_um_count_kernel(const i32 *__restrict__ map, i64 n, int tile_rows, i64 cells,
+                                                           u32 *__restrict__ counts, unsigned long long *__restrict__ n_real) {
+    const int lane = threadIdx.x & 31;
+    const i64 cell = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);           // = tile * 126 + k; k == 125 is the zero pad of the scan
+    if (cell >= cells) return;
+    const i64 t = cell / (GPC_K3 + 1);
+    const int k = (int)(cell - t * (GPC_K3 + 1));
+    u32 c = 0;
+    if (k < GPC_K3) {
+        const i64 r0 = t * tile_rows;
+        const int rows = (int)min((i64)tile_rows, n - r0);
+        const i32 *m = map + (i64)k * n + r0;
+        for (int r = lane; r < rows; r += 32) c += m[r] >= 0;
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
     }
-    return m;
+    if (lane == 0) {
+        counts[cell] = (c + 15u) & ~15u;
+        if (c) atomicAdd(n_real, (unsigned long long)c);
+    }
 }
-
-__global__ void __launch_bounds__(256) kmap_rt8_count_kernel(const i32 *__restrict__ map, i64 n, u8 *__restrict__ hdr,
-                                                            u32 *__restrict__ counts) {
-    const i64 st = blockIdx.x;
-    const i64 r0 = st * RT_TW;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = warp; k < 128; k += 8) {
-        u32 m = 0;
-        if (k < GPC_K3) { i32 v0, v1; m = rt8_mask(map, n, r0, k, lane, v0, v1); }
-        if (lane == 0) {
-            hdr[st * 128 + k] = (u8)m;
-            if (k <= GPC_K3) counts[st * (GPC_K3 + 1) + k] = __popc(m);
+__global__ void __launch_bounds__(128) kmap_um_fill_kernel(const i32 *__restrict__ map, i64 n, int tile_rows, i64 cells,
+                                                          const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr, u32 *__restrict__ pair_off) {
+    const int lane = threadIdx.x & 31;
+    const i64 cell = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (cell >= cells) return;
+    const i64 t = cell / (GPC_K3 + 1);
+    const int k = (int)(cell - t * (GPC_K3 + 1));
+    if (k >= GPC_K3) return;
+    u32 p = seg[cell];
+    const u32 end = seg[cell + 1];
+    if (p == end) return;
+    const i64 r0 = t * tile_rows;
+    const int rows = (int)min((i64)tile_rows, n - r0);
+    const i32 *m = map + (i64)k * n + r0;
+    const u32 lt = (1u << lane) - 1u;
+    for (int rb = 0; rb < rows; rb += 32) {                               // ascending row order inside a cell
+        const int r = rb + lane;
+        const i32 nb = r < rows ? m[r] : -1;
+        const u32 bal = __ballot_sync(0xFFFFFFFFu, nb >= 0);
+        if (nb >= 0) {
+            const u32 q = p + __popc(bal & lt);
+            pair_nbr[q] = (u32)nb;
+            pair_off[q] = (u32)r * 128u;
         }
+        p += __popc(bal);
+    }
+    for (u32 q = p + lane; q < end; q += 32) {                            // padding
+        pair_nbr[q] = 0xFFFFFFFFu;
+        pair_off[q] = (u32)tile_rows * 128u;
     }
 }
-__global__ void __launch_bounds__(256) kmap_rt8_fill_kernel(const i32 *__restrict__ map, i64 n, const u32 *__restrict__ toff,
-                                                           u32 *__restrict__ tiles) {
-    const i64 st = blockIdx.x;
-    const i64 r0 = st * RT_TW;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = warp; k < GPC_K3; k += 8) {
-        i32 v0, v1;
-        const u32 m = rt8_mask(map, n, r0, k, lane, v0, v1);
-        if (!m) continue;
-        const u32 base = toff[st * (GPC_K3 + 1) + k];
-        const int j0 = lane >> 3, j1 = 4 + (lane >> 3);
-        if ((m >> j0) & 1u) tiles[(i64)(base + __popc(m & ((1u << j0) - 1u))) * 8 + (lane & 7)] = (u32)v0;   // -1 -> 0xFFFFFFFF
-        if ((m >> j1) & 1u) tiles[(i64)(base + __popc(m & ((1u << j1) - 1u))) * 8 + (lane & 7)] = (u32)v1;
-    }
-}
-extern "C" size_t gpc_kmap_rt8_workspace_bytes(int64_t n) {
-    const i64 nst = n > 0 ? (n + RT_TW - 1) / RT_TW : 1;
-    const i64 m = nst * (GPC_K3 + 1);
-    return align_up((size_t)m * 4, 256) + align_up(scan_workspace_bytes<u32>(m), 256) + 1024;
-}
-extern "C" int gpc_kmap_rt8_count(const int32_t *map, int64_t n, uint8_t *hdr, uint32_t *toff, uint32_t *n_tiles, void *ws,
-                                  size_t ws_bytes, void *stream) {
+extern "C" size_t gpc_kmap_um_workspace_bytes(int64_t n, int tile_rows) { return gpc_kmap_pairs_workspace_bytes(n, tile_rows); }
+// totals: device u64[2] = {stream entries (padded), true pairs}
+extern "C" int gpc_kmap_um_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals, void *ws,
+                                 size_t ws_bytes, void *stream) {
     cudaStream_t st = as_stream(stream);
-    if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(n_tiles, 0, 4, st)); return GPC_OK; }
-    GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_rt8_workspace_bytes(n), GPC_ENOSPC, "workspace too small");
-    const i64 nst = (n + RT_TW - 1) / RT_TW;
-    const i64 m = nst * (GPC_K3 + 1);
+    GPC_REQUIRE(tile_rows >= 32 && tile_rows <= 1024, GPC_EINVAL, "tile_rows must be in 32..1024");
+    GPC_CUDA_CHECK(cudaMemsetAsync(totals, 0, 16, st));
+    if (n <= 0) return GPC_OK;
+    GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_um_workspace_bytes(n, tile_rows), GPC_ENOSPC, "workspace too small");
+    const i64 tiles = (n + tile_rows - 1) / tile_rows;
+    const i64 m = tiles * (GPC_K3 + 1);
     u32 *counts = (u32 *)ws;
     void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
-    kmap_rt8_count_kernel<<<(unsigned)nst, 256, 0, st>>>(map, n, hdr, counts);
+    kmap_um_count_kernel<<<cdiv(m, 4), 128, 0, st>>>(map, n, tile_rows, m, counts, totals + 1);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{counts};
-    int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, toff, scan_ws, st);
+    int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, seg, scan_ws, st);      // seg has m + 1 entries
     if (rc) return rc;
-    kmap_total_kernel<<<1, 1, 0, st>>>(toff, m, n_tiles);
-    GPC_LAUNCH_CHECK();
+    GPC_CUDA_CHECK(cudaMemcpyAsync(totals, seg + m, 4, cudaMemcpyDeviceToDevice, st));
     return GPC_OK;
 }
-extern "C" int gpc_kmap_rt8_fill(const int32_t *map, int64_t n, const uint32_t *toff, uint32_t *tiles, void *stream) {
+extern "C" int gpc_kmap_um_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr,
+                                uint32_t *pair_off, void *stream) {
     if (n <= 0) return GPC_OK;
-    const i64 nst = (n + RT_TW - 1) / RT_TW;
-    kmap_rt8_fill_kernel<<<(unsigned)nst, 256, 0, as_stream(stream)>>>(map, n, toff, tiles);
+    const i64 tiles = (n + tile_rows - 1) / tile_rows;
+    const i64 m = tiles * (GPC_K3 + 1);
+    kmap_um_fill_kernel<<<cdiv(m, 4), 128, 0, as_stream(stream)>>>(map, n, tile_rows, m, seg, pair_nbr, pair_off);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }

@@ -573,7 +573,7 @@ static int launch_spconv_um(const CUtensorMap &tmap, const CUtensorMap &tmap_g, 
 }
 
 // xs = split rows [n][128 B]; Wp = this conv's slice of gpc_spconv_pack_weights_um; seg / pair_nbr = the pair stream built with
-// tile_rows (512 or 1024) and pad = 16 (padding entries 0xFFFFFFFF), pair_off = gpc_kmap_row_offsets of its pair_row.  Output rows
+// tile_rows (512 or 1024) and pad = 16 (padding entries 0xFFFFFFFF), pair_off (gpc_kmap_um_count / _fill).  Output rows
 // [row0, row1) (whole tiles; row1 <= 0 or >= n: to the end).  y (fp32 rows) and / or ys (split rows).
 extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr,
                                  const uint32_t *pair_off, int64_t n, int tile_rows, const void *residual, int flags, float *y,
@@ -620,18 +620,6 @@ extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t 
     }
     if (prof) return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
     return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
-}
-
-// pair_row (u16 row within the tile, 0xFFFF = padding) -> byte offset of the pair's accumulator row: row * 128, padding -> the dummy row
-__global__ void row_offsets_kernel(const u16 *__restrict__ pair_row, i64 n_entries, u32 tile_rows, u32 *__restrict__ out) {
-    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_entries) { const u32 r = pair_row[g]; out[g] = (r == 0xFFFFu ? tile_rows : r) * 128u; }
-}
-extern "C" int gpc_kmap_row_offsets(const uint16_t *pair_row, int64_t n_entries, int tile_rows, uint32_t *pair_off, void *stream) {
-    if (n_entries <= 0) return GPC_OK;
-    row_offsets_kernel<<<cdiv(n_entries, 256), 256, 0, as_stream(stream)>>>(pair_row, n_entries, (u32)tile_rows, pair_off);
-    GPC_LAUNCH_CHECK();
-    return GPC_OK;
 }
 
 // W [n_kernels*125][32 ci][32 co] fp32 -> Wp [n_kernels*125][8 chunks][32 co][4 words]: channel co's TMEM lane is 32 words = 8 chunks of

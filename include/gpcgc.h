@@ -132,35 +132,13 @@ int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows, const uint
 /* y[o,:] = act( sum_k x[nbr_k(o),:] . W[k] (+ residual[o,:]) ); W [125,32,32] fp32;
  * offsets accumulate in ascending k for every row (deterministic). flags: bit0 = ReLU. */
 #define GPC_CONV_RELU 1
-/* variant 0: unpipelined FFMA kernel, W in the reference layout [125,32,32].
- * variant >= 1: cp.async-pipelined FFMA2 kernels; W must be the packed form produced by
- * gpc_spconv_pack_weights ([125,16,32] float2 = (W[2i][co], W[2i+1][co])).
- * tile_rows must match the pair lists (gpc_kmap_pairs_*). */
-int gpc_spconv_pack_weights(const float *W, int n_kernels, float *W_packed, void *stream);
-int gpc_spconv_fwd(const float *x, const float *W, const uint32_t *seg, const uint32_t *pair_nbr,
-                   const uint16_t *pair_row, int64_t n, int tile_rows, const float *residual,
-                   int flags, float *y, int variant, void *stream);
-
-/* v3 kernels (variant 10..): fixed-size gather blocks over the combined pair stream, warp-owned rows */
-int gpc_spconv_fwd_v3(const float *x, const float *W_packed, const uint32_t *seg, const uint64_t *pairs,
-                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
-                      void *stream);
-
-/* v4 kernels (variant 20..): one warp per sub-tile of `tile_rows` rows, split-bf16 mma.sync contraction
- * with fp32 accumulation; Wb from gpc_spconv_pack_weights_bf16 ([125][2][8][32] x 4 bf16, hi and lo halves) */
-int gpc_spconv_pack_weights_bf16(const float *W, int n_kernels, void *Wb, void *stream);
-int gpc_spconv_fwd_v4(const float *x, const void *Wb, const uint32_t *seg, const uint64_t *pairs,
-                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
-                      void *stream);
-
-/* v5 kernels (variant 30..): as v4 with W^T as the MMA A operand (8-pair granularity);
- * Wa from gpc_spconv_pack_weights_frag ([125][2][2][2][32] uint4 fragment order) */
+/* Wa [n_kernels*125][2][2][2][32] uint4: the mma.m16n8k16 A fragments of W[k]^T, bf16 hi and lo halves (one LDG.128 per lane) */
 int gpc_spconv_pack_weights_frag(const float *W, int n_kernels, void *Wa, void *stream);
-int gpc_spconv_fwd_v5(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
-                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
-                      void *stream);
 
-/* v6 kernels (variant 40..): software-pipelined v5 over a stream padded to 8-entry tiles (pad = 8) */
+/* the mma.sync conv (spconv.cu): one warp per tile of tile_rows output rows over the combined pair stream padded to 8-entry MMA tiles
+ * (pad = 8), W^T[k] as the MMA A operand, the gathered rows as the B operand (bf16 hi / lo split, three terms, fp32 accumulation).
+ * variant 42: cp.async gather ring; 45 / 46 / 47: the offsets of a tile split over 2 / 8 / 16 warps (coarse levels); 48: rows loaded
+ * straight into the MMA fragments (v6d, big levels) */
 int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
                       int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                       void *stream);
@@ -171,22 +149,6 @@ int gpc_spconv_fwd_v6(const float *x, const void *Wa, const uint32_t *seg, const
 int gpc_spconv_fwd_v6_rows(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
                            int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
                            int64_t row0, int64_t row1, void *stream);
-
-/* row-tied kernel map ("rt8") + v7 conv (variant 50..): sub-tiles of 64 rows = 8 groups of 8 rows;
- * hdr[st*128 + k] = mask of groups with a neighbour at offset k; toff[st*126 + k] = first 8-entry tile of
- * (st,k) in `tiles` (u32 input rows, 0xFFFFFFFF = absent); accumulators stay in registers */
-size_t gpc_kmap_rt8_workspace_bytes(int64_t n);
-int gpc_kmap_rt8_count(const int32_t *map, int64_t n, uint8_t *hdr, uint32_t *toff, uint32_t *n_tiles,
-                       void *ws, size_t ws_bytes, void *stream);
-int gpc_kmap_rt8_fill(const int32_t *map, int64_t n, const uint32_t *toff, uint32_t *tiles, void *stream);
-int gpc_spconv_fwd_v7(const float *x, const void *Wa, const uint32_t *toff, const uint8_t *hdr,
-                      const uint32_t *tiles, int64_t n, const float *residual, int flags, float *y,
-                      int variant, void *stream);
-
-/* v8 (variant 60): v6 with the per-tile instruction count cut (ping-pong register sets, 32-bit shared addressing) */
-int gpc_spconv_fwd_v8(const float *x, const void *Wa, const uint32_t *seg, const uint64_t *pairs,
-                      int64_t n, int tile_rows, const float *residual, int flags, float *y, int variant,
-                      void *stream);
 
 /* ---- the conv of the SPARSE big levels (spconv_sparse.cu): dense centre product + offset-sorted "stragglers" ----
  * For levels with ~1-4 neighbours per row (the finest octree levels).  Sparse map: seg u32[gpc_kmap_sparse_segments(n) + 1]
@@ -209,24 +171,11 @@ int gpc_spconv_sparse_fwd_rows(const float *x, const void *Wa, const uint32_t *s
                                int64_t n, int64_t n_entries, float *contrib, const float *residual, int flags, float *y,
                                int64_t row0, int64_t row1, void *stream);
 
-/* ---- the tcgen05 sparse conv (spconv_tc.cu, spconv_fmt.cu): the kernel the big octree levels run ---- */
-/* "split rows": an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits) -- a gathered
- * row is a tensor-core operand row as it stands */
+/* ---- split rows (spconv_fmt.cu): an activation row stored as 32 x bf16 hi | 32 x bf16 lo (128 B, x = hi + lo to 16 mantissa bits):
+ * a gathered row is a tensor-core operand row as it stands */
 int gpc_rows_split(const float *x, int64_t n, void *xs, void *stream);
 int gpc_rows_join(const void *xs, int64_t n, float *x, void *stream);
-/* Wc [n_kernels*125][4 KB]: per offset the canonical K-major (no swizzle) bf16 tiles of W[k]^T, hi then lo */
-int gpc_spconv_pack_weights_umma(const float *W, int n_kernels, void *Wc, void *stream);
-/* y[o,:] = act( sum_k W[k]^T xs[nbr_k(o),:] (+ residual[o,:]) ) with the contraction on the 5th-generation tensor cores:
- * 17 warps per CTA (8 gather, 1 tcgen05.mma issue, 8 scatter-add); the gathered rows are the MMA's A operand in tensor memory,
- * W[k] its B operand in shared memory, accumulators D in tensor memory, per-row fp32 sums in shared memory (fixed order).
- * xs = split rows; CTA tiles of cta_rows (512 / 1024) output rows = 4 quarters; seg / pairs = the pair stream built with
- * tile_rows = cta_rows / 4 and pad = 1.  Outputs: y (fp32 rows) and / or ys (split rows), either may be NULL.
- * flags: GPC_CONV_RELU, GPC_CONV_RES_SPLIT (residual points to split rows, else fp32 rows).
- * profile != 0 runs the instrumented build whose per-role cycle counters gpc_debug_conv_tc_profile returns (host u64[16]). */
-#define GPC_CONV_RES_SPLIT 2
-int gpc_spconv_fwd_tc(const void *xs, const void *Wc, const uint32_t *seg, const uint64_t *pairs, int64_t n,
-                      int cta_rows, const void *residual, int flags, float *y, void *ys, int profile, void *stream);
-int gpc_debug_conv_tc_profile(unsigned long long *out_h, int reset);
+#define GPC_CONV_RES_SPLIT 2   /* conv flags bit: residual points to split rows (else fp32 rows) */
 
 /* ---- the tcgen05 sparse conv of the big levels (spconv_um.cu) ----
  * y[o,:] = act( sum_k W[k]^T xs[nbr_k(o),:] (+ residual[o,:]) ).  Transposed formulation: per (tile of tile_rows output rows, offset k)
@@ -235,27 +184,35 @@ int gpc_debug_conv_tc_profile(unsigned long long *out_h, int reset);
  * memory, D in tensor memory; the epilogue adds every pair to its output row's fp32 sum in shared memory, offsets ascending (one
  * fixed summation order per row).
  * xs = split rows; Wp = this conv's slice of gpc_spconv_pack_weights_um ([125][32 co][128 B]); seg / pair_nbr = the pair stream
- * (gpc_kmap_pairs_*) built with tile_rows = 512 or 1024 and pad = 16, pair_off = gpc_kmap_row_offsets(pair_row).  Outputs y (fp32
+ * and accumulator-row offsets built by gpc_kmap_um_count / _fill with tile_rows = 256, 384, 512 or 1024.  Outputs y (fp32
  * rows) and / or ys (split rows).  Only the output rows [row0, row1) are computed (whole tiles; row1 <= 0 or >= n: to the end):
  * the decoder wavefront.  flags: GPC_CONV_RELU, GPC_CONV_RES_SPLIT, GPC_CONV_PROFILE. */
 #define GPC_CONV_PROFILE 256   /* flags bit: run the instrumented build (per-role cycle counters, gpc_debug_conv_um_profile) */
 int gpc_debug_conv_um_profile(unsigned long long *out_h, int reset);
 int gpc_spconv_pack_weights_um(const float *W, int n_kernels, void *Wp, void *stream);
-/* pair_row (row within the tile, 0xFFFF = padding) -> byte offset of the pair's accumulator row (row * 128; padding -> dummy row) */
-int gpc_kmap_row_offsets(const uint16_t *pair_row, int64_t n_entries, int tile_rows, uint32_t *pair_off, void *stream);
+/* pair stream of gpc_spconv_fwd_um, straight from the dense map (one warp per (tile, offset) cell): seg as gpc_kmap_pairs_count with
+ * pad = 16; pair_nbr = input row (padding 0xFFFFFFFF), pair_off = byte offset of the accumulator row, row_in_tile * 128 (padding: the
+ * dummy row tile_rows * 128).  totals = device u64[2]: {stream entries (padded), true pairs}. */
+size_t gpc_kmap_um_workspace_bytes(int64_t n, int tile_rows);
+int gpc_kmap_um_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals, void *ws,
+                      size_t ws_bytes, void *stream);
+int gpc_kmap_um_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr, uint32_t *pair_off,
+                     void *stream);
 int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr, const uint32_t *pair_off,
                       int64_t n, int tile_rows, const void *residual, int flags, float *y, void *ys, int64_t row0, int64_t row1,
                       void *stream);
 
 /* ---- a-6/a-9/a-12: embeddings ---- */
+/* Every producer of conv inputs writes fp32 rows (out), split rows (out_split: 32 x bf16 hi | 32 x bf16 lo, the operand format of
+ * gpc_spconv_fwd_um) or both; either pointer may be NULL. */
 /* out[o,:] = table[idx[o],:]  (prior_embedding, network_ue_4stage_conv.py:15) */
-int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *stream);
+int gpc_embed_rows(const uint8_t *idx, int64_t n, const float *table, float *out, void *out_split, void *stream);
 /* out[j,:] = feat[parent[j],:] + temb[octant(child_key[j]),:]  (FCG replicate + TargetEmbedding) */
 int gpc_gather_parent_add_octant(const float *feat, const uint32_t *parent, const uint64_t *child_keys,
-                                 int64_t n_child, const float *temb, float *out, void *stream);
+                                 int64_t n_child, const float *temb, float *out, void *out_split, void *stream);
 /* out[o,:] = u[o,:] + emb[occ[o] >> shift, :]   (pred_head_s{1,2,3}_emb; shift = 7, 6, 4) */
 int gpc_add_ctx_embed(const float *u, const uint8_t *occ, int shift, const float *emb, int64_t n,
-                      float *out, void *stream);
+                      float *out, void *out_split, void *stream);
 
 /* ---- a-12/a-13: fused head: Linear-ReLU-Linear-softmax-cumsum-quantise ---- */
 /* cdf [n, A+1] uint16 (int16 bit pattern of kit/op.py:67-79); prob [n, A] optional (may be NULL) */

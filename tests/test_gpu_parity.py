@@ -146,15 +146,22 @@ def test_kernel_map(env, n, seed, ext):
     xyz = uniform_unique_cloud(n, seed, extent_log2=ext) if ext < 10 else hac_like_cloud(n, seed, extent_log2=ext)
     xyz = xyz[O.sort_zyx_perm(xyz)]
     keys, _ = _keys_of(codec, xyz)
-    km, dense = codec.build_kmap(keys, keep_dense=True)
+    from gauspcc_b200.codec import _ptr
+    dense = codec.dense_map(keys)
     ref = O.kmap(xyz, 5)
     assert np.array_equal(dense.cpu().numpy().T, ref)                   # dense map, canonical indexing
     # pair lists: segment (tile, k) lists exactly the rows with a neighbour at k, ascending
-    seg = km.seg.cpu().numpy().astype(np.int64)
-    nbr = km.pair_nbr.cpu().numpy()
-    row = km.pair_row.cpu().numpy().astype(np.int64) & 0xFFFF
-    assert km.n_pairs == int((ref >= 0).sum()) == seg[-1]
-    tr = km.tile_rows
+    tr = 64
+    seg_t, n_pairs, n_real = codec._count_pairs(dense, n, tr, 1)
+    nbr_t = torch.empty((max(n_pairs, 1),), dtype=torch.int32, device=codec.dev)
+    row_t = torch.empty((max(n_pairs, 1),), dtype=torch.int16, device=codec.dev)
+    codec._call("gpc_kmap_pairs_fill", _ptr(dense), n, tr, _ptr(seg_t), _ptr(nbr_t), _ptr(row_t), None, 0, codec._stream())
+    seg = seg_t.cpu().numpy().astype(np.int64)
+    nbr = nbr_t.cpu().numpy()
+    row = row_t.cpu().numpy().astype(np.int64) & 0xFFFF
+    assert n_pairs == n_real == int((ref >= 0).sum()) == seg[-1]
+    # the conv's own map counts the same pairs
+    assert codec.build_kmap(keys).n_real == n_real
     for t in range((n + tr - 1) // tr):
         sub = ref[t * tr:(t + 1) * tr]
         for k in (0, 31, 62, 63, 124):
@@ -225,7 +232,6 @@ def test_sparse_conv_centre_stragglers(env_sparse, n, ext):
     xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
     xyz = xyz[O.sort_zyx_perm(xyz)]
     keys, _ = _keys_of(codec, xyz)
-    codec._seen_sparse = True
     km = codec.build_kmap(keys)
     assert km.sparse
     ref_km = O.kmap(xyz, 5)
@@ -255,9 +261,10 @@ def env_v6d(env):
     with >= 150 K rows of a full-size scene take."""
     from gauspcc_b200.codec import GausPcgcCodec
     codec = GausPcgcCodec(env["codec"].w, env["dev"], tile_rows=128)
-    codec.conv_variant = 48
+    codec.v6_variant = 48
+    codec.um_min_rows = codec.sparse_min_rows = 1 << 40                     # every level on the mma.sync conv
     codec6 = GausPcgcCodec(env["codec"].w, env["dev"], tile_rows=64)       # v6, one warp per 64-row tile, on every level
-    codec6.conv_variant = 42
+    codec6.um_min_rows = codec6.sparse_min_rows = 1 << 40
     return dict(env, codec=codec, codec6=codec6)
 
 
@@ -290,7 +297,6 @@ def test_sparse_conv_v6d(env_v6d, n, ext, tile):
         assert np.abs(y2 - np.maximum(ref + res, 0)).max() <= 2e-5 * scale
         assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)            # deterministic
         base = env_v6d["codec6"]
-        base.sparse_max_density = 0
         km6 = base.build_kmap(keys)
         assert km6.v6_variant == 42 and km6.tile_rows == 64
         assert np.array_equal(base.conv(xd, 7, km6).cpu().numpy(), y)            # v6: same sums bit for bit
@@ -306,29 +312,31 @@ def test_codec_v6d_vs_oracle(env_v6d, n, seed, ext):
 
 @pytest.fixture(scope="module")
 def env_umma(env):
-    """A second codec whose levels ALL run the tcgen05 conv (split rows), whatever their size and density."""
+    """A second codec whose levels ALL run the tcgen05 conv (spconv_um.cu, split rows), whatever their size and density."""
     from gauspcc_b200.codec import GausPcgcCodec
     codec = GausPcgcCodec(env["codec"].w, env["dev"])
-    codec.conv_variant = 100
-    codec.tc_min_rows, codec.tc_min_density = 1, 0.0
+    codec.um_min_rows, codec.sparse_max_density = 1, 0.0
     return dict(env, codec=codec)
 
 
-@pytest.mark.parametrize("n,ext,cta_rows", [(30000, 16, 1024), (30000, 16, 512), (2000, 6, 1024), (1025, 5, 1024), (77, 4, 512)])
-def test_sparse_conv_tcgen05(env_umma, n, ext, cta_rows):
-    """tcgen05 / TMEM conv over split rows against the fp32 oracle conv: fp32 and split outputs, residual in both formats."""
+@pytest.mark.parametrize("n,ext,tile", [(30000, 16, 512), (30000, 16, 384), (30000, 16, 256), (30000, 16, 1024), (2000, 6, 512),
+                                        (1025, 5, 1024), (513, 5, 512), (77, 4, 512)])
+def test_sparse_conv_tcgen05(env_umma, n, ext, tile):
+    """tcgen05 / TMEM conv over split rows against the fp32 oracle conv: fp32 and split outputs, residual in both formats, row-range
+    launches (decoder wavefront) bit-identical to the whole launch, ragged last tile."""
     from gauspcc_b200.codec import _ptr
     from gauspcc_b200.synth import hac_like_cloud, uniform_unique_cloud
     from oracle import oracle as O
     codec, w = env_umma["codec"], env_umma["w"]
-    codec.tc_cta_rows = cta_rows
+    codec.um_tile_rows = tile
     try:
         xyz = uniform_unique_cloud(n, 5, extent_log2=ext) if ext < 10 else hac_like_cloud(n, 5, extent_log2=ext)
         xyz = xyz[O.sort_zyx_perm(xyz)]
         keys, _ = _keys_of(codec, xyz)
         km = codec.build_kmap(keys)
-        assert km.cta_rows == cta_rows and km.tile_rows == cta_rows // 4
+        assert km.um_rows == tile and km.tile_rows == tile
         ref_km = O.kmap(xyz, 5)
+        assert km.n_real == int((ref_km >= 0).sum())
         rng = np.random.default_rng(0)
         x = rng.normal(size=(n, 32)).astype(np.float32)
         res = rng.normal(size=(n, 32)).astype(np.float32)
@@ -349,8 +357,15 @@ def test_sparse_conv_tcgen05(env_umma, n, ext, cta_rows):
         assert np.abs(y3 - y2).max() <= 3e-5 * scale
         # deterministic: bit-identical on a second launch (encoder / decoder CDF identity depends on it)
         assert np.array_equal(codec.conv(xd, 7, km).cpu().numpy(), y)
+        # row ranges (whole tiles): the same sums bit for bit
+        if n > tile:
+            cut = (n // 2) // tile * tile or tile
+            yr = torch.full((n, 32), float("nan"), device=codec.dev)
+            codec.conv(xs, 7, km, out=yr, rows=(0, cut))
+            codec.conv(xs, 7, km, out=yr, rows=(cut, n))
+            assert np.array_equal(yr.cpu().numpy(), y)
     finally:
-        codec.tc_cta_rows = 1024
+        codec.um_tile_rows = 512
 
 
 @pytest.mark.parametrize("n,seed,ext", [(20000, 1, 16), (2500, 5, 12)])
@@ -548,16 +563,16 @@ def test_cli_file_roundtrip(env, tmp_path):
 
 
 @pytest.mark.parametrize("plane", [True, False])
-@pytest.mark.parametrize("kind", ["v6d", "sparse"])
-def test_decoder_wavefront(env, env_v6d, env_sparse, kind, plane):
+@pytest.mark.parametrize("kind", ["um", "v6d", "sparse"])
+def test_decoder_wavefront(env, env_v6d, env_sparse, env_umma, kind, plane):
     """The decoder's stage wavefront (chunks of rows, four range-decoder threads) against the stage-by-stage decode of the same
     streams: identical geometry row for row; levels of every chunk count (ragged last chunk, levels that fail the halo check or are
-    too small fall back).  Both conv families that support row ranges."""
+    too small fall back).  All three conv families of the big levels."""
     from gauspcc_b200.codec import GausPcgcCodec
     from gauspcc_b200.synth import hac_like_cloud
-    src = (env_v6d if kind == "v6d" else env_sparse)["codec"]
+    src = {"v6d": env_v6d, "sparse": env_sparse, "um": env_umma}[kind]["codec"]
     codec = GausPcgcCodec(src.w, env["dev"], tile_rows=128 if kind == "v6d" else None)
-    codec.conv_variant = src.conv_variant
+    codec.v6_variant, codec.um_min_rows = src.v6_variant, src.um_min_rows
     codec.sparse_min_rows, codec.sparse_max_density = src.sparse_min_rows, src.sparse_max_density
     codec.wave_min_rows, codec.wave_chunk_rows = 1, 8192
     codec.wave_plane_lag = plane                       # stage i+1 trails stage i by planes (default) / by two chunks

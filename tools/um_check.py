@@ -36,9 +36,7 @@ def main():
         n = lv.n
         if n < min_rows:
             continue
-        codec._seen_sparse = False
-        codec.sparse_max_density = 0.0                 # reference conv: v6 / v6d on every level
-        km6, dense = codec.build_kmap(lv.keys, keep_dense=True)
+        dense = codec.dense_map(lv.keys)
         g = torch.Generator(device=dev).manual_seed(li)
         x = torch.randn((n, 32), device=dev, generator=g)
         res = torch.randn((n, 32), device=dev, generator=g)
@@ -56,7 +54,7 @@ def main():
         ref_relu = torch.relu(ref + res.double())
         n_pairs_real = int((dense >= 0).sum())
         # v6d timing
-        km6b = codec.build_kmap(lv.keys)
+        km6b = codec.build_kmap(lv.keys, family="v6")
         y6 = codec.conv(x, widx, km6b, residual=res, relu=True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -69,10 +67,8 @@ def main():
         err6 = float((y6.double() - torch.relu((ref - xj.double().new_zeros(1)) + res.double())).abs().max())
         for tr in tiles:
             tmag, gflag = 0, 0
-            km = codec._pair_stream(dense, n, tr, 16, True)
-            km._fill()
-            poff = torch.empty((max(km.n_pairs, 1),), dtype=torch.int32, device=dev)
-            _lib.check(lib.gpc_kmap_row_offsets(_ptr(km.pair_row), km.n_pairs, tr, _ptr(poff), st), "row_offsets")
+            km = codec._um_map(dense, n, tr)
+            poff = km.pair_off
             y = torch.full((n, 32), float("nan"), device=dev)
             ys = torch.zeros((n, 32), dtype=torch.int32, device=dev)
             args = (_ptr(xs), _ptr(wp[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(poff), n, tr, _ptr(res), 1 | gflag, _ptr(y), _ptr(ys), 0, 0, st)
