@@ -8,21 +8,29 @@ A "step" is one pass of the hot path over one scene: device-resident voxel ancho
 kernel maps -> 18 sparse convs + 4 heads per level -> CDF rows (encode), then the same on the decode
 side driven by the decoded symbols.  Workload at N=1: BASELINE config[1], 1M synthetic anchors with
 the sparse-global/dense-local HAC++ distribution.  At N>1 the path shards by scene: every rank codes
-its own 1M-anchor scene (seed = rank), no data-path collective, one small all_gather of per-scene
-results ("scaling": "weak").
+its own copy of THE SAME scene (seed 0 on every rank: the max over ranks then measures the box, not the
+luck of a rank's scene), no data-path collective, one small all_gather of per-scene results
+("scaling": "weak").
 
-value   = Mpoints/s, CUDA-event time of K steps (encode + decode device stages; CDFs stay in HBM;
-          the decode side is fed the true symbols from HBM instead of the host range decoder, the
-          device work is identical -- tests/test_gpu_parity.py proves the real decode is lossless).
-e2e     = same metric through the public API (pcc_utils.compress_point_cloud /
-          decompress_point_cloud) with HOST input, host range coder, file write/read and the result
-          read back to the host, wall clock.
+value    = Mpoints/s, CUDA-event time of K steps (encode + decode device stages; CDFs stay in HBM;
+           the decode side is fed the true symbols from HBM instead of the host range decoder, the
+           device work is identical -- tests/test_gpu_parity.py proves the real decode is lossless).
+           Nothing else is recorded inside the timed region.
+e2e      = same metric through the public API (pcc_utils.compress_point_cloud /
+           decompress_point_cloud) with HOST input, host range coder, file write/read and the result
+           read back to the host, wall clock.  This is the number to hold against the reference arm.
+roofline = the dominant kernel family of the step (the sparse conv of the big dense levels), from a SEPARATE
+           profiled step after the timed region: algorithmic bytes / CUDA-event time of exactly
+           those launches; `traffic` = measured dram bytes per launch of the same kernel from the committed
+           ncu capture (profiles/r02_conv_um_dram.json).  `per_stage` lists every stage of the step the same way.
 --impl reference: the reference algorithm on the host cores (CPU oracle port; the reference's own
-          dependencies torchsparse/torchac are not installable offline), same metric/config.
+           dependencies torchsparse/torchac are not installable offline) on the SAME workload when the
+           run fits the time budget, else on the largest sample that does (config.sample_points says which).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -38,7 +46,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mpoints/s GausPcgc encode+decode (device-timed)"
 UNIT = "Mpoints/s"
-CPU_SAMPLE_POINTS = 50_000
+DTYPE = "bf16x3-split/f32-acc"        # every product is hi.hi + hi.lo + lo.hi of bf16 halves (16 mantissa bits), fp32 accumulation
+REF_BUDGET_S = 330.0                  # the reference arm's whole run (warm-up + steps) stays within a few minutes
+CPU_BASELINE_S = 15.0                 # the cpu_baseline leg of the repo arm: one bounded sample
 
 
 def _peaks():
@@ -46,6 +56,10 @@ def _peaks():
     if os.path.exists(p):
         return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def _workload(points: int) -> str:
+    return f"GausPcgc encode/decode, {points} synthetic anchors (sparse-global/dense-local HAC++ distribution)"
 
 
 class ClockSampler(threading.Thread):
@@ -77,43 +91,84 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_reference_throughput(points: int, seed: int, steps: int = 1, warmup: int = 0):
-    """The reference algorithm (CPU oracle port) on the host cores -> (Mpoints/s, seconds per step, cores)."""
+# ----------------------------------------------------------------------------- the reference algorithm on the host cores
+def _host_threads() -> int:
+    """All the cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its ranks; the oracle's OpenMP runtime is told the
+    real number explicitly (libgomp is the runtime the oracle's shared library links)."""
+    n = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
+def _oracle_roundtrip(xyz, w):
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    blob = O.encode(xyz, w)
+    dec = O.decode(blob, w)
+    dt = time.perf_counter() - t0
+    assert dec.shape[0] == xyz.shape[0], "oracle round trip lost points"
+    return dt
+
+
+def cpu_reference(points: int, steps: int, warmup: int, budget_s: float):
+    """The CPU oracle port (reference algorithm, all host cores) on `points` anchors of the bench scene if warm-up + steps fit the
+    budget, else on the largest sample that does.  -> (Mpoints/s, s per step, cores, sample points)"""
     from gauspcc_b200.synth import hac_like_cloud
     from gauspcc_b200.weights import make_synthetic_state_dict, state_dict_to_numpy
-    from oracle import oracle as O
+    cores = _host_threads()
     w = state_dict_to_numpy(make_synthetic_state_dict())
-    xyz = hac_like_cloud(points, seed)
+    cal_n = min(points, 20_000)
+    cal = _oracle_roundtrip(hac_like_cloud(cal_n, 0), w)                 # calibration: seconds per point on this box (also warms the library)
+    per_point = cal / cal_n
+    fit = int(budget_s / max(steps + warmup, 1) / per_point * 0.9)        # the oracle is a little super-linear: keep some slack
+    sample = points if fit >= points else max(cal_n, fit // 10_000 * 10_000)
+    xyz = hac_like_cloud(sample, 0)
     times = []
     for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        blob = O.encode(xyz, w)
-        dec = O.decode(blob, w)
-        dt = time.perf_counter() - t0
-        assert dec.shape[0] == points
+        dt = _oracle_roundtrip(xyz, w)
         if it >= warmup:
             times.append(dt)
     sec = float(np.mean(times))
-    return points / sec / 1e6, sec, len(os.sched_getaffinity(0))
+    return sample / sec / 1e6, sec, cores, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
-    val, sec, cores = cpu_reference_throughput(CPU_SAMPLE_POINTS, 0, steps=args.steps, warmup=args.warmup)
-    sample = f"{CPU_SAMPLE_POINTS} anchors of the same HAC-like distribution per step (encode+decode, lossless checked by size)"
+        return                                                           # one CPU arm per box: the host cores are shared by the ranks
+    val, sec, cores, sample = cpu_reference(args.points, args.steps, args.warmup, REF_BUDGET_S)
+    note = (f"{sample} anchors of the bench scene per step (encode+decode, lossless checked)"
+            + ("" if sample == args.points else f": the full {args.points}-anchor config does not fit {REF_BUDGET_S:.0f} s for "
+               f"{args.warmup}+{args.steps} steps on {cores} cores"))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GausPcgc encode/decode, {args.points} synthetic anchors (sparse-global/dense-local HAC++ distribution), "
-                               f"reference algorithm on host cores over a bounded sample", "sample_points": CPU_SAMPLE_POINTS},
-        "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": _workload(args.points) + ", reference algorithm (CPU port) on the box's host cores", "sample_points": sample,
+                   "same_config": sample == args.points,
+                   "box_level": "one scene at a time on all host cores; the value is the whole box's CPU throughput whatever --gpus says"},
+        "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": cores, "kind": "port", "sample": note},
         "e2e": {"value": round(val, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- the repo arm
+def _pin_rank(local: int, world: int):
+    """cores / world CPUs per rank (contiguous slice of the affinity mask): 8 ranks x (16 range-coder threads + the launch thread) on
+    32 unpinned cores was what bent the end-to-end scaling curve in round 1"""
+    cpus = sorted(os.sched_getaffinity(0))
+    if world <= 1 or len(cpus) < 2 * world:
+        return len(cpus)
+    per = len(cpus) // world
+    mine = cpus[local * per:(local + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return len(mine)
 
 
 def main():
@@ -125,10 +180,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_cpus = _pin_rank(local, world)                                 # before torch / the codec size their thread pools
 
     import torch
     import torch.distributed as dist
@@ -137,9 +198,6 @@ def main():
     from gauspcc_b200.synth import hac_like_cloud
     from gauspcc_b200.weights import make_synthetic_state_dict, save_synthetic_checkpoint
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     dev = torch.device("cuda", local)
@@ -149,7 +207,7 @@ def main():
 
     sd = make_synthetic_state_dict()
     codec = GausPcgcCodec(DeviceWeights(sd, dev), dev)
-    xyz = hac_like_cloud(args.points, seed=rank)                     # one scene per rank (weak scaling by scene)
+    xyz = hac_like_cloud(args.points, seed=0)                        # the same scene on every rank (weak scaling by scene)
     x_dev = torch.tensor(xyz, dtype=torch.float32, device=dev)       # resident in HBM before the timed region
     from gauspcc_b200.pcc_utils import calculate_morton_order
     x_dev = x_dev[calculate_morton_order(x_dev)]                     # as HAC hands it over (gaussian_model.py:1108-1109)
@@ -168,16 +226,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    codec.conv_profile = []                                          # also makes build_kmap count the true pairs
+    codec.conv_profile = None
     for _ in range(args.warmup):
         n_out, _, _ = step()
     assert n_out == args.points
     barrier()
-    codec.prewarm_profile_events(2 * (len(codec.conv_profile) // max(args.warmup, 1) + 8) * args.steps)     # 2 events per conv group
     sampler = ClockSampler(local)
     if not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
-    codec.conv_profile = [] if not os.environ.get("BENCH_NO_PROFILE") else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     t_wall0 = time.perf_counter()
@@ -192,12 +248,6 @@ def main():
     if sampler.is_alive():
         sampler.join()
     ms = e0.elapsed_time(e1)
-    prof = codec.conv_profile or []
-    codec.conv_profile = None
-    conv_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
-    conv_bytes = sum(p[2] for p in prof)
-    conv_flops = sum(p[3] for p in prof)
-    conv_launches = sum(p[4] for p in prof)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # max over ranks
@@ -210,15 +260,37 @@ def main():
     ms_per_step = ms_max / args.steps
     value = total_points / (ms_per_step / 1e3) / 1e6
 
+    # ---- per-stage profile: two extra steps OUTSIDE the timed region, one CUDA-event pair per stage instance
+    stages = {}
+    if rank == 0 and not args.no_profile:
+        n_prof = 2
+        codec.conv_profile = []
+        step()                                                       # creates the events of the pool
+        codec.prewarm_profile_events(2 * len(codec.conv_profile) + 64)
+        codec.conv_profile = []
+        for _ in range(n_prof):
+            codec._ev_next = 0
+            pre = len(codec.conv_profile)
+            step()
+            torch.cuda.synchronize(dev)
+            for p in codec.conv_profile[pre:]:
+                st = stages.setdefault(p[5], {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0, "instances": 0})
+                st["ms"] += p[0].elapsed_time(p[1]) / n_prof
+                st["bytes"] += p[2] / n_prof
+                st["flops"] += p[3] / n_prof
+                st["launches"] += p[4] / n_prof
+                st["instances"] += 1 / n_prof
+        codec.conv_profile = None
+
     # ---- e2e through the public API, host buffers in, host result out (rank-local scene, wall clock)
     e2e = None
     if not args.no_e2e:
         tmp = tempfile.mkdtemp(prefix="gpcgc_bench_")
         ckpt = save_synthetic_checkpoint(os.path.join(tmp, "GausPcgc", "best_model_ue_4stage_conv.pt"))
         x_host = x_dev.cpu().pin_memory()
-        binp = os.path.join(tmp, "xyz_pcc.bin")
+        binp = os.path.join(tmp, f"xyz_pcc_{rank}.bin")
         n_e2e = max(1, min(args.steps, 3))
-        walls, d2h = [], 0
+        walls = []
         for it in range(1 + n_e2e):
             barrier()
             t0 = time.perf_counter()
@@ -241,41 +313,56 @@ def main():
                "enc_s": round(r["enc_time"], 4), "dec_s": round(d["dec_time"], 4), "bpp": round(r["bpp"], 3),
                "dec_host_ac_s": round(dec_stats.get("host_ac_s", 0.0), 4), "dec_gpu_wait_s": round(dec_stats.get("gpu_wait_s", 0.0), 4),
                "dec_gpu_s": round(dec_stats.get("gpu_ms", 0.0) / 1e3, 4), "dec_wavefront_levels": int(dec_stats.get("wave_levels", 0)),
-               "ac_threads": codec.pool._max_workers}
+               "ac_threads": codec_threads(pcc_utils), "cpus_per_rank": n_cpus}
         assert pts_host.shape[0] == args.points
 
     if rank == 0:
         peaks, peak_kind = _peaks()
-        achieved = conv_bytes / (conv_ms / 1e3) / 1e9 if conv_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"GausPcgc encode/decode, {args.points} synthetic anchors (sparse-global/dense-local HAC++ "
-                                   f"distribution), 1 scene per B200", "points_per_gpu": args.points, "levels": n_levels,
-                       "symbol_rows": n_symbol_rows, "tile_rows": codec.tile_rows,
+            "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": _workload(args.points) + ", 1 scene per B200", "points_per_gpu": args.points, "levels": n_levels,
+                       "symbol_rows": n_symbol_rows, "same_scene_on_every_rank": True,
                        "l2": "working set (>= 128 MB feature arrays per level) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"scene-sharded x{world}", "wall_ms_per_step": round(t_wall * 1e3 / args.steps, 2)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "spconv_um (tcgen05) + sp_centre / sp_straggler + spconv_fwd_v6",
-                         "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
-                         "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-                         # dram__bytes_read+write of the profiled launch (442 133-row level, spconv_fwd_v6d<128>: 145.4 + 31.4 MB) / its
-                         # algorithmic bytes (187.9 MB) = 0.94 (profiles/r01_spconv_v6_ncu_summary.md); scaled to the average launch of this run
-                         "traffic": round(0.94 * conv_bytes / max(conv_launches, 1)),
-                         "note": "all sparse-conv launches of the step; the dominant kernel (spconv_fwd_v6d<128>, 56 % of the step) is not HBM-bound: "
-                                 "L1/shared path 69 %, issue 41 %, HMMA pipe 30 %, 10 of 12 resident warps per SM, latency-bound (ncu, final capture); "
-                                 "see DESIGN.md 5",
-                         "launches": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4), "event_pairs": len(prof),
-                         "share_of_step": round(conv_ms / ms, 4), "tflops_fp32": round(conv_flops / (conv_ms / 1e3) / 1e12, 2) if conv_ms else 0},
         }
+        if stages:
+            per_stage, tot_ms = [], sum(v["ms"] for v in stages.values())
+            for name, v in sorted(stages.items(), key=lambda kv: -kv[1]["ms"]):
+                gbs = v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0
+                per_stage.append({"stage": name, "ms_per_step": round(v["ms"], 3), "share": round(v["ms"] / tot_ms, 4),
+                                  "algorithmic_mb": round(v["bytes"] / 1e6, 1), "gbs": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4),
+                                  "launches": int(round(v["launches"])) or int(round(v["instances"]))})
+            dom_name = per_stage[0]["stage"]
+            dom = stages[dom_name]
+            achieved = dom["bytes"] / (dom["ms"] / 1e3) / 1e9
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r02_conv_um_dram.json")
+            if dom_name == "conv_um" and os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                traffic, traffic_src = int(tj["dram_bytes_per_launch_mean"]), "profiles/r02_conv_um_dram.json (ncu --set full, same kernel, same scene)"
+            kernels = {"conv_um": "spconv_um_kernel<512, 64, ...> (tcgen05.mma + TMA gather4 / tile loads, big dense levels)",
+                       "conv_sparse": "sp_centre_kernel + sp_straggler_kernel (sparse big levels)", "conv_v6": "spconv_fwd_v6 / v6d (mma.sync, coarse levels)"}
+            line["roofline"] = {"kernel": kernels.get(dom_name, dom_name), "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                                "peak_kind": peak_kind + " (burst copy figure)", "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+                                "traffic": traffic, "traffic_source": traffic_src,
+                                "algorithmic_bytes_per_launch": int(dom["bytes"] / max(dom["launches"], 1)),
+                                "avg_launch_ms": round(dom["ms"] / max(dom["launches"], 1), 4), "launches_per_step": int(round(dom["launches"])),
+                                "share_of_profiled_step": per_stage[0]["share"],
+                                "tflops_effective_fp32": round(dom["flops"] / (dom["ms"] / 1e3) / 1e12, 2),
+                                "note": "measured in two separate profiled steps (one CUDA-event pair per group of convs on a level) after the timed "
+                                        "region; the kernel is bound by its warp-specialised pipeline (hand-offs and the MMA-issue warp), not by HBM: "
+                                        "profiles/r02_conv_um.md"}
+            line["per_stage"] = per_stage
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline:
-            val, sec, cores = cpu_reference_throughput(CPU_SAMPLE_POINTS, 0)
-            line["cpu_baseline"] = {"value": round(val, 5), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{CPU_SAMPLE_POINTS} anchors, same distribution, encode+decode once ({sec:.1f} s)"}
+            val, sec, cores, sample = cpu_reference(args.points, 1, 0, CPU_BASELINE_S)
+            line["cpu_baseline"] = {"value": round(val, 5), "unit": UNIT, "cores": cores, "kind": "port", "same_config": sample == args.points,
+                                    "sample": f"{sample} anchors of the bench scene, encode+decode once ({sec:.1f} s) on {cores} host threads"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -285,6 +372,12 @@ def codec_stats(pcc_utils_mod):
     for c in pcc_utils_mod._CODECS.values():
         return dict(c.last_stats)
     return {}
+
+
+def codec_threads(pcc_utils_mod):
+    for c in pcc_utils_mod._CODECS.values():
+        return c.pool._max_workers
+    return 0
 
 
 if __name__ == "__main__":

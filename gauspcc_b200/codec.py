@@ -350,6 +350,11 @@ class GausPcgcCodec:
         km.contrib = self._empty((max(n_strag, 1), 32), torch.float32)
         return km
 
+    @staticmethod
+    def _kmap_bytes(n: int) -> int:
+        """hash build n*12 + cap*12 (cap = 2n), probes n*K^3*8; the pair stream adds pairs*12 (not known here)"""
+        return n * 12 + 2 * n * 12 + n * 125 * 8
+
     def dense_map(self, keys: torch.Tensor) -> torch.Tensor:
         """hash table of the level + the offset-major [125][n] map of input rows (-1 = absent)"""
         n = keys.shape[0]
@@ -443,7 +448,7 @@ class GausPcgcCodec:
             return None
         e0, e1 = self._profile_events()
         e0.record(torch.cuda.current_stream(self.dev))
-        self._prof_group = [e0, e1, 0, 0, 0]
+        self._prof_group = [e0, e1, 0, 0, 0, "conv"]
         return self._prof_group
 
     def _prof_close(self, grp):
@@ -452,6 +457,26 @@ class GausPcgcCodec:
         grp[1].record(torch.cuda.current_stream(self.dev))
         self.conv_profile.append(tuple(grp))
         self._prof_group = None
+
+    def _stage(self, name: str, nbytes: int = 0):
+        """bench.py's per-stage profile: one CUDA-event pair around a non-conv stage (algorithmic bytes per SURVEY.md 8(d))"""
+        codec = self
+
+        class _Ctx:
+            def __enter__(self_):
+                self_.g = None
+                if codec.conv_profile is not None and codec._prof_group is None:
+                    e0, e1 = codec._profile_events()
+                    e0.record(torch.cuda.current_stream(codec.dev))
+                    self_.g = (e0, e1)
+                return self_
+
+            def __exit__(self_, *a):
+                if self_.g is not None:
+                    self_.g[1].record(torch.cuda.current_stream(codec.dev))
+                    codec.conv_profile.append((self_.g[0], self_.g[1], int(nbytes), 0, 0, name))
+                return False
+        return _Ctx()
 
     def _prof_conv_begin(self):
         self._prof_single = self._prof_open()          # None inside a group (or when not profiling)
@@ -463,6 +488,7 @@ class GausPcgcCodec:
             g[2] += n * 32 * 4 * 2 + km.n_real * 8 + 125 * 32 * 32 * 4
             g[3] += 2 * km.n_real * 32 * 32
             g[4] += 1
+            g[5] = "conv_um" if km.um_rows else ("conv_sparse" if km.sparse else "conv_v6")
         self._prof_close(self._prof_single)
         self._prof_single = None
 
@@ -492,18 +518,25 @@ class GausPcgcCodec:
         child_kmap: the kernel map of the child set if the caller has built it already (encoder).
         Returns (child level, u): u = fp32 rows, or (fp32 rows, split rows) on a tcgen05 level."""
         if parent.kmap is None:
-            parent.kmap = self.build_kmap(parent.keys)
+            with self._stage("kmap", self._kmap_bytes(parent.n)):
+                parent.kmap = self.build_kmap(parent.keys)
         pum = bool(parent.kmap.um_rows)
         f = self._empty((parent.n, 32), torch.int32 if pum else torch.float32)
-        self._call("gpc_embed_rows", _ptr(parent.occ), parent.n, _ptr(self.w.prior_emb), None if pum else _ptr(f), _ptr(f) if pum else None,
-                   self._stream())
+        with self._stage("embed", parent.n * 129):
+            self._call("gpc_embed_rows", _ptr(parent.occ), parent.n, _ptr(self.w.prior_emb), None if pum else _ptr(f), _ptr(f) if pum else None,
+                       self._stream())
         f = self.res_stack(f, W.PRIOR_CONVS, parent.kmap)            # fp32 rows (the children gather them)
-        ck, cp = self.expand(parent, n_child)
-        child = Level(ck, None, n_child, child_kmap if child_kmap is not None else self.build_kmap(ck))
+        with self._stage("expand", parent.n * 33 + n_child * 12):
+            ck, cp = self.expand(parent, n_child)
+        if child_kmap is None:
+            with self._stage("kmap", self._kmap_bytes(n_child)):
+                child_kmap = self.build_kmap(ck)
+        child = Level(ck, None, n_child, child_kmap)
         cum = bool(child.kmap.um_rows)
         u0 = self._empty((n_child, 32), torch.int32 if cum else torch.float32)
-        self._call("gpc_gather_parent_add_octant", _ptr(f), _ptr(cp), _ptr(ck), n_child, _ptr(self.w.target_emb), None if cum else _ptr(u0),
-                   _ptr(u0) if cum else None, self._stream())
+        with self._stage("embed", n_child * (12 + 4 + 256)):
+            self._call("gpc_gather_parent_add_octant", _ptr(f), _ptr(cp), _ptr(ck), n_child, _ptr(self.w.target_emb), None if cum else _ptr(u0),
+                       _ptr(u0) if cum else None, self._stream())
         # tcgen05 level: u is needed as fp32 rows (context embeddings) and as split rows (stage 0 conv input)
         u = self.res_stack(u0, W.TARGET_CONVS, child.kmap, final="both" if cum else "f32")
         return child, u
@@ -520,20 +553,22 @@ class GausPcgcCodec:
             f = u_split if um else u
         else:
             f = self._empty((n, 32), torch.int32 if um else torch.float32)
-            self._call("gpc_add_ctx_embed", _ptr(u), _ptr(occ_partial), CTX_SHIFT[i], _ptr(self.w.stage_emb[i]), n, None if um else _ptr(f),
-                       _ptr(f) if um else None, self._stream())
+            with self._stage("embed", n * 257):
+                self._call("gpc_add_ctx_embed", _ptr(u), _ptr(occ_partial), CTX_SHIFT[i], _ptr(self.w.stage_emb[i]), n, None if um else _ptr(f),
+                           _ptr(f) if um else None, self._stream())
         c0, c1 = W.stage_convs(i)
         grp = self._prof_open()
         t = self.conv(f, c0, km, relu=True, fmt="split" if um else "f32")
         t = self.conv(t, c1, km)
         self._prof_close(grp)
         w1, b1, w2, b2 = self.w.head[i]
-        if lohi_out is not None:
-            self._call("gpc_head_cdf_sym", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(occ_partial),
-                       STAGE_SHIFT[i], _ptr(lohi_out), _ptr(cdf_out), _ptr(prob_out), self._stream())
-        else:
-            self._call("gpc_head_cdf", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(cdf_out),
-                       _ptr(prob_out), self._stream())
+        with self._stage("head", n * (128 + 2 * (W.STAGE_ALPHABETS[i] + 1))):
+            if lohi_out is not None:
+                self._call("gpc_head_cdf_sym", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(occ_partial),
+                           STAGE_SHIFT[i], _ptr(lohi_out), _ptr(cdf_out), _ptr(prob_out), self._stream())
+            else:
+                self._call("gpc_head_cdf", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(cdf_out),
+                           _ptr(prob_out), self._stream())
 
     # ------------------------------------------------------------------ host range coder
     def _ac_encode(self, cdf: np.ndarray, sym: np.ndarray) -> bytes:
@@ -574,15 +609,19 @@ class GausPcgcCodec:
         self._stream_h = torch.cuda.current_stream(self.dev).cuda_stream
         self._seg_begin()
         xyz = xyz.contiguous()
-        keys, meta = self.pack_keys(xyz)
+        n_in = int(xyz.shape[0])
+        with self._stage("order", n_in * 20 + 6 * n_in * 24):            # pack + 6-pass radix sort + unique (SURVEY 8d radix model)
+            keys, meta = self.pack_keys(xyz)
         meta_h = meta.cpu().numpy()
         if meta_h[0] & 1:
             raise ValueError("compress_point_cloud expects voxelised (integral) coordinates")
         if meta_h[0] & 2:
             raise ValueError(f"voxel coordinates must lie within +-{(1 << 20) - 16}")
         mm = meta_h[2:8].astype(np.uint32)
-        leaf = self.sort_unique(keys, mm)
-        levels = self.build_pyramid(leaf, mm.astype(np.int64))
+        with self._stage("order", 0):
+            leaf = self.sort_unique(keys, mm)
+        with self._stage("pyramid", int(leaf.shape[0]) * (25 + 6 * 24) * 8 // 7):   # geometric sum over the levels: n_l*12 + n_(l+1)*13 + one sort of n_l pairs
+            levels = self.build_pyramid(leaf, mm.astype(np.int64))
         L = len(levels) - 1
         rows = sum(l.n for l in levels[1:])
         arena = self._pin(rows * 16 + 64 * 4 * max(L, 1) + 4096) if download else None
@@ -604,7 +643,8 @@ class GausPcgcCodec:
         if L:
             for lv in levels:
                 if lv.kmap is None:
-                    lv.kmap = self.build_kmap(lv.keys)
+                    with self._stage("kmap", self._kmap_bytes(lv.n)):
+                        lv.kmap = self.build_kmap(lv.keys)
         level_futs = [[] for _ in range(L)]
         if collect:
             aux["child_keys"], aux["probs"], aux["cdfs"] = [None] * L, [None] * (4 * L), [None] * (4 * L)
@@ -628,7 +668,7 @@ class GausPcgcCodec:
                     aux["probs"][4 * d + i] = prob_d
                     aux["cdfs"][4 * d + i] = cdf_d
             if download:
-                ready = torch.cuda.Event()
+                ready = torch.cuda.Event(blocking=True)          # the coder threads sleep on it instead of spinning
                 ready.record(torch.cuda.current_stream(self.dev))
                 # host range coding of this level overlaps the GPU work of the coarser levels
                 level_futs[d] = [self.pool.submit(self._ac_encode_lohi, h.numpy().view(np.uint32), ready) for h in level_jobs]
@@ -801,8 +841,8 @@ class GausPcgcCodec:
             w1, b1, w2, b2 = heads[i]
             call("gpc_head_cdf", p_t1[i] + r0 * 128, r1 - r0, w1, b1, w2, b2, W.STAGE_ALPHABETS[i], p_cdf_d[i] + r0 * Lps[i] * 2, None, SH[i])
             call("gpc_copy_async", p_cdf_h[i] + r0 * Lps[i] * 2, p_cdf_d[i] + r0 * Lps[i] * 2, (r1 - r0) * Lps[i] * 2, SH[i])
-            ev = torch.cuda.Event()
-            ev.record(S[i])
+            ev = torch.cuda.Event(blocking=True)               # decoder thread i sleeps on it (a spinning waiter per stage stole the cores
+            ev.record(S[i])                                    # the launch thread needs)
             ev_q[i].put(ev)
 
         plane = self.wave_plane_lag
