@@ -125,6 +125,7 @@ class GausPcgcCodec:
         self._wave_side: Optional[list] = None
         self._wave_buf: Optional[torch.Tensor] = None
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
+        self.debug_dec_cdfs: Optional[dict] = None    # tests: (level, stage) -> CDF rows the stage-by-stage decoder computed
         self.wave_first_rows = 8192                   # size / number of the small leading chunks
         self.wave_first_chunks = 0                    # measured: small leading chunks cost more than they save (dec 0.242 vs 0.218 s)
         self._launch_base = 0
@@ -982,6 +983,8 @@ class GausPcgcCodec:
                 A = W.STAGE_ALPHABETS[i]
                 cdf_d = self._empty((n_child, A + 1), torch.int16)
                 self.stage_cdf(u, occ, i, child.kmap, cdf_d)
+                if self.debug_dec_cdfs is not None:            # tests: the decoder's CDF rows of every (level, stage)
+                    self.debug_dec_cdfs[(g // 4, i)] = cdf_d
                 if forced_occ is not None:
                     sym_d = self._empty((n_child,), torch.uint8)
                     self._call("gpc_split_symbol", _ptr(forced_occ[g // 4]), n_child, STAGE_SHIFT[i], STAGE_MASK[i], _ptr(sym_d),

@@ -29,9 +29,6 @@
 #include <cuda.h>
 #include "umma.cuh"
 
-#ifndef UM_EPI_ROWS
-#define UM_EPI_ROWS 0        // 1: an epilogue warp owns output rows (no barrier, column ranges by ballot); 0: it owns columns (one barrier per chunk)
-#endif
 #ifndef UM_GATHER_TMA
 #define UM_GATHER_TMA 1      // 1: the rows of the non-centre offsets by TMA tile::gather4 (A/B, profiles/r02_conv_um.md); 0: cp.async
 #endif
@@ -47,7 +44,7 @@
 
 template <int TM, int NMAX, int GS, int DS, int WS, int NPW>
 struct UmSmem {
-    float acc[TM + 1][GPC_C];                          // row TM: dummy row (target of padding pairs and of columns outside a warp's range)
+    float acc[TM + 16][GPC_C];                         // rows TM ..: one dummy row per epilogue warp (target of padding pairs, never read)
     __align__(1024) unsigned char g[GS][NMAX * 128];   // gathered rows of a chunk (128 B swizzle atoms of 8 rows)
     __align__(16) u32 roff[GS + DS][NMAX];             // byte offset of every pair's accumulator row (row * 128; padding -> dummy row)
     __align__(16) u32 idx[NPW][4][NMAX];               // per producer: input rows of the pairs of its next chunks
@@ -319,105 +316,17 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             if (lane == 0) mbar_arrive(full_w0 + ws * 8);
         }
     } else {
-#if UM_EPI_ROWS
-        // =================================================================== epilogue: warp e owns the output rows [e ER, (e + 1) ER) of the
-        // tile.  The pairs of a chunk are sorted by output row, so the warp's pairs are ONE column range of D, found with two ballots
-        // over the chunk's row offsets; it is read in aligned groups of 8 columns (lane = channel, register = pair) and every pair is
-        // added to its row with one conflict-free 128 B read-modify-write.  No warp waits for another: a row has one owner, and the
-        // owner meets the chunks in offset order.
-        constexpr u32 ER = TM / NEW;
-        const u32 e = (u32)warp - 8u;
-        const u32 lo = e * ER * 128u, hi = lo + ER * 128u;       // my rows as accumulator byte offsets
-        const u32 acc0 = (u32)__cvta_generic_to_shared(&s.acc[0][0]) + (u32)lane * 4u;
-        const u32 dummy = (u32)TM * 128u;
-        const u32 td = tmem + ((((u32)warp & 3u) * 32u) << 16);  // my lane quadrant
-        // The warp's work is a stream of ITEMS = aligned groups of 8 columns inside its range, chunk after chunk.  An item's D columns
-        // and row offsets are requested (tcgen05.ld is asynchronous) while the previous item is added to its rows.
-        u32 c = 0xFFFFFFFFu, col = 0, c0 = 0, c1 = 0;            // current chunk, next group, my range
-        u32 issued = 0, released = 0;                            // chunks whose groups are all requested / handed back
-        u32 n_items = 0;
-        const u32 *ro = nullptr;
-        auto wait_release = [&]() {                              // every requested load has landed: hand back the chunks that are fully requested
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (released < issued) {
-                tmem_fence_before();
-                __syncwarp();
-                for (; released < issued; ++released)
-                    if (lane == 0) mbar_arrive(empty_d0 + (released % (u32)DS) * 8);
-            }
-        };
-        auto load_item = [&](u32 (&d)[8], u32 (&ra)[8]) -> bool {
-            while (col >= c1) {                                  // next chunk with columns of mine
-                if (c != 0xFFFFFFFFu) ++issued;
-                ++c;
-                if (c >= n_chunks) return false;
-                if (issued - released >= 2u) wait_release();     // never block on a later chunk while holding two (the MMA warp needs chunk c - DS back)
-                const u32 ds = c % (u32)DS, len = (s.tab[c] >> 12) & 0xFFu;
-                UM_T(t2);
-                UM_WAIT(full_d0 + ds * 8, (c / (u32)DS) & 1u);
-                tmem_fence_after();
-                UM_T(t3);
-                UM_ACC(1, t2, t3);
-                ro = &s.roff[c % (u32)RS][0];
-                u32 n0 = 0, n1 = 0;
-#pragma unroll
-                for (int i = 0; i < NMAX / 32; ++i) {
-                    const u32 cc = (u32)(i * 32 + lane);
-                    const u32 r = cc < len ? ro[cc] : dummy;     // padding entries point at the dummy row (>= every hi)
-                    n0 += __popc(__ballot_sync(0xFFFFFFFFu, r < lo));
-                    n1 += __popc(__ballot_sync(0xFFFFFFFFu, r < hi));
-                }
-                c0 = n0; c1 = n1; col = n0 & ~7u;
-            }
-            UM_T(t2);
-            tmem_ld8(td + (c % (u32)DS) * NMAX + col, d);
-            UM_T(t3);
-            UM_ACC(2, t2, t3);
-            const uint4 r0 = *reinterpret_cast<const uint4 *>(ro + col), r1 = *reinterpret_cast<const uint4 *>(ro + col + 4);
-            const u32 rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) ra[jj] = acc0 + ((col + jj >= c0 && col + jj < c1) ? rr[jj] : dummy);
-            col += 8;
-            return true;
-        };
-        auto rmw = [&](const u32 (&d)[8], const u32 (&ra)[8]) {
-            UM_T(t2);
-            float a[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) a[jj] = um_lds(ra[jj]);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) um_sts(ra[jj], a[jj] + __uint_as_float(d[jj]));
-            asm volatile("" ::: "memory");
-            UM_T(t3);
-            UM_ACC(3, t2, t3);
-            if (PROF) ++n_items;
-        };
-        u32 dA[8], dB[8], raA[8], raB[8];
-        UM_T(t0);
-        bool more = n_chunks != 0 && load_item(dA, raA);
-        wait_release();
-        while (more) {
-            const bool moreB = load_item(dB, raB);
-            rmw(dA, raA);
-            wait_release();
-            if (!moreB) break;
-            more = load_item(dA, raA);
-            rmw(dB, raB);
-            wait_release();
-        }
-        // chunks behind my last item (no columns of mine) are handed back by the loads above; make sure all are
-        if (n_chunks) { issued = n_chunks; wait_release(); }
-        UM_T(t1);
-        UM_ACC(0, t0, t1);
-#else
         // =================================================================== epilogue: warp e adds the columns [CPW e, CPW e + CPW) of every
         // chunk to their rows.  Within a chunk the rows are distinct; a barrier between chunks keeps the offsets of a row in order.
         constexpr int CPW = NMAX / NEW;                          // 8 or 16 columns of a chunk per warp
         const u32 e = (u32)warp - 8u;
         const u32 acc0 = (u32)__cvta_generic_to_shared(&s.acc[0][0]) + (u32)lane * 4u;
         const u32 td = tmem + ((((u32)warp & 3u) * 32u) << 16) + e * CPW;       // my lane quadrant, my columns
-        // load(c): my D columns and row offsets of chunk c -> registers (asynchronous); done(c): wait for them and hand the D buffer back
-        auto load = [&](u32 c, u32 (&d)[CPW], uint4 (&r)[CPW / 4], bool &on) {
+        // load(c): my D columns (asynchronous) and the accumulator addresses of my pairs of chunk c -> registers; a padding entry
+        // (offset of row TM) goes to this warp's own dummy row.  done(c): wait for the columns and hand the D buffer back -- the
+        // row offsets have been consumed by then (the address arithmetic below), so their ring slot may be rewritten.
+        const u32 pad_off = (u32)TM * 128u, my_dummy = acc0 + ((u32)TM + e) * 128u;
+        auto load = [&](u32 c, u32 (&d)[CPW], u32 (&ra)[CPW], bool &on) {
             const u32 ds = c % (u32)DS;
             on = e * CPW < ((s.tab[c] >> 12) & 0xFFu);           // len is a multiple of 16: my columns are inside or outside
             UM_WAIT(full_d0 + ds * 8, (c / (u32)DS) & 1u);
@@ -427,30 +336,34 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 else tmem_ld8(td + ds * NMAX, *reinterpret_cast<u32(*)[8]>(&d[0]));
                 const uint4 *ro = reinterpret_cast<const uint4 *>(&s.roff[c % (u32)RS][e * CPW]);
 #pragma unroll
-                for (int i = 0; i < CPW / 4; ++i) r[i] = ro[i];
+                for (int i = 0; i < CPW / 4; ++i) {
+                    const uint4 r = ro[i];
+                    ra[4 * i] = r.x >= pad_off ? my_dummy : acc0 + r.x;
+                    ra[4 * i + 1] = r.y >= pad_off ? my_dummy : acc0 + r.y;
+                    ra[4 * i + 2] = r.z >= pad_off ? my_dummy : acc0 + r.z;
+                    ra[4 * i + 3] = r.w >= pad_off ? my_dummy : acc0 + r.w;
+                }
             }
         };
         auto done = [&](u32 c) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tmem_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_d0 + (c % (u32)DS) * 8);     // values and row offsets are in registers: hand the buffer back
+            if (lane == 0) mbar_arrive(empty_d0 + (c % (u32)DS) * 8);     // values and addresses are in registers: hand the buffer back
         };
-        auto rmw = [&](const u32 (&d)[CPW], const uint4 (&r)[CPW / 4], bool on) {
+        auto rmw = [&](const u32 (&d)[CPW], const u32 (&ra)[CPW], bool on) {
             if (on) {
 #pragma unroll
                 for (int h = 0; h < CPW / 8; ++h) {
-                    const u32 ro[8] = {r[2 * h].x, r[2 * h].y, r[2 * h].z, r[2 * h].w, r[2 * h + 1].x, r[2 * h + 1].y, r[2 * h + 1].z, r[2 * h + 1].w};
                     float a[8];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) a[jj] = um_lds(acc0 + ro[jj]);
+                    for (int jj = 0; jj < 8; ++jj) a[jj] = um_lds(ra[8 * h + jj]);
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) um_sts(acc0 + ro[jj], a[jj] + __uint_as_float(d[8 * h + jj]));
+                    for (int jj = 0; jj < 8; ++jj) um_sts(ra[8 * h + jj], a[jj] + __uint_as_float(d[8 * h + jj]));
                 }
             }
         };
-        u32 dA[CPW], dB[CPW];
-        uint4 rA[CPW / 4], rB[CPW / 4];
+        u32 dA[CPW], dB[CPW], rA[CPW], rB[CPW];
         bool onA = false, onB = false;
         UM_T(t0);
         if (n_chunks) { load(0, dA, rA, onA); done(0); }
@@ -470,7 +383,6 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         asm volatile("" ::: "memory");
         UM_T(t1);
         UM_ACC(0, t0, t1);
-#endif
         if (warp == 8) { UM_FLUSH(7, 0); UM_FLUSH(8, 1); UM_FLUSH(9, 2); UM_FLUSH(10, 3); }
         asm volatile("" ::: "memory");
     }
