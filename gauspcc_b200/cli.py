@@ -7,8 +7,8 @@
 Same argument names, file discovery (recursive, sorted, h5 / ply / bin / npy; compress_ue_4stage_conv.py:57-63), coordinate
 mapping (`x / 0.001 + 131072` unless pre-quantised, then `round(x / posQ)`, :90-95; inverse `(c * posQ - 131072) * 0.001`,
 decompress_ue_4stage_conv.py:176-179), `.bin` container (one `<name>.bin` per input) and CSV report (`<prefix>_data<N>.csv` with a
-final `avg` row, :253-276) as the reference scripts.  Differences: the library is built for channels = 32, kernel_size = 5 (the HAC
-call sites) and says so for anything else; point files are read in this process (the reference forks 64 workers); `h5` is not
+final `avg` row, :253-276) as the reference scripts.  `--kernel_size` defaults to 3 as in the reference scripts
+(compress_ue_4stage_conv.py:44; the HAC call sites use 5, pcc_utils.py:29): both are built, channels = 32 only.  Differences: point files are read in this process (the reference forks 64 workers); `h5` is not
 read (the reference lists the suffix but `kit/io.py:read_points` cannot parse it either).  No torchsparse / torchac.
 """
 from __future__ import annotations
@@ -126,7 +126,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         sp.add_argument("--ckpt", required=True, help="Network(32, 5).state_dict() checkpoint")
         sp.add_argument("--is_data_pre_quantized", action="store_true", help="inputs are integer voxel coordinates already")
         sp.add_argument("--channels", type=int, default=32)
-        sp.add_argument("--kernel_size", type=int, default=5)
+        sp.add_argument("--kernel_size", type=int, default=3)      # the reference scripts' default; the checkpoint must match
         sp.add_argument("--resultdir", default=None, help="folder for the CSV report")
         sp.add_argument("--prefix", default="ue_4stage_conv")
         if cmd == "compress":

@@ -67,13 +67,19 @@ class DeviceWeights:
     """state_dict (reference key layout, gauspcc_b200/weights.py) resident in HBM."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, channels: int = 32, kernel_size: int = 5):
-        if channels != 32 or kernel_size != 5:
-            raise NotImplementedError("libgpcgc is built for channels=32, kernel_size=5 (the reference call sites)")
+        if channels != 32 or kernel_size not in (3, 5):
+            raise NotImplementedError("libgpcgc is built for channels=32 and kernel_size 5 (HAC call sites) or 3 (the reference CLI default)")
         W.validate_state_dict(sd, channels, kernel_size)
+        self.kernel_size = kernel_size
         f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32).contiguous()
         self.prior_emb = f("prior_embedding.weight")
         self.target_emb = f("target_embedding.target_res_embedding.weight")
-        self.convs = torch.stack([f(k) for k in W.CONV_KEYS]).contiguous()           # [18,125,32,32]
+        self.convs = torch.stack([f(k) for k in W.CONV_KEYS]).contiguous()           # [18,K^3,32,32]
+        if kernel_size == 3:       # the 27 matrices at their K = 5 offset indices ((dz+2)*5 + (dy+2))*5 + (dx+2); the kernel map drops the rest
+            k5 = [((dz + 2) * 5 + (dy + 2)) * 5 + (dx + 2) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+            full = torch.zeros((len(W.CONV_KEYS), 125, 32, 32), dtype=torch.float32, device=device)
+            full[:, torch.tensor(k5, device=device)] = self.convs
+            self.convs = full.contiguous()
         lib = _lib.load()
         st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         self.convs_frag = torch.empty_like(self.convs)       # [18,125,2,2,2,32] uint4: mma.sync A fragments of W^T (bf16 hi / lo)
@@ -362,8 +368,8 @@ class GausPcgcCodec:
         cap = self.lib.gpc_hash_capacity(n)
         table = self._ws(cap * 16)
         self._call("gpc_hash_build", _ptr(keys), n, _ptr(table), cap, self._stream())
-        dense = self._empty((W.reference_layout()["prior_resnet.0.kernel"][0], n), torch.int32)
-        self._call("gpc_kmap_dense", _ptr(table), cap, _ptr(keys), n, _ptr(dense), self._stream())
+        dense = self._empty((125, n), torch.int32)
+        self._call("gpc_kmap_dense", _ptr(table), cap, _ptr(keys), n, _ptr(dense), self.w.kernel_size, self._stream())
         return dense
 
     def build_kmap(self, keys: torch.Tensor, family: Optional[str] = None) -> KMap:
@@ -1024,13 +1030,13 @@ class GausPcgcCodec:
         return out
 
 
-_WEIGHT_CACHE: Dict[Tuple[str, float, str], DeviceWeights] = {}
+_WEIGHT_CACHE: Dict[tuple, DeviceWeights] = {}
 
 
 def load_weights(ckpt_path: str, device: torch.device, channels: int = 32, kernel_size: int = 5) -> DeviceWeights:
     """torch.load the checkpoint once per (path, mtime, device); the reference reloads on every call
     (pcc_utils.py:65-67).  Missing file -> FileNotFoundError, bad layout -> RuntimeError, as there."""
-    key = (os.path.abspath(ckpt_path), os.path.getmtime(ckpt_path), str(device))
+    key = (os.path.abspath(ckpt_path), os.path.getmtime(ckpt_path), str(device), channels, kernel_size)
     if key not in _WEIGHT_CACHE:
         sd = torch.load(ckpt_path, map_location="cpu")
         _WEIGHT_CACHE[key] = DeviceWeights(sd, device, channels, kernel_size)

@@ -92,13 +92,20 @@ extern "C" int gpc_hash_lookup(const void *table, int64_t capacity, const uint64
     return GPC_OK;
 }
 
-// one thread per (row o, line (dz,dy)); blockIdx.y = line, so every one of the 5 output planes is written coalesced
+// one thread per (row o, line (dz,dy)); blockIdx.y = line, so every one of the 5 output planes is written coalesced.
+// half = kernel_size / 2: offsets with a component beyond it are absent (-1) without a probe -- a K = 3 conv
+// (compress_ue_4stage_conv.py:44) runs on the K = 5 machinery with its 27 offsets at their K = 5 indices.
 __global__ void kmap_dense_kernel(const HashSlot *__restrict__ table, u32 mask, const u64 *__restrict__ keys, i64 n,
-                                  i32 *__restrict__ map) {
+                                  i32 *__restrict__ map, int half) {
     const int line = blockIdx.y;                      // (dz+2)*5 + (dy+2)
     i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n) return;
     const int dy = line % 5 - 2, dz = line / 5 - 2;
+    if (abs(dy) > half || abs(dz) > half) {
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) map[(i64)(line * 5 + dx) * n + o] = -1;
+        return;
+    }
     // fields never under/overflow: |c| <= 2^20 - 16
     const u64 k0 = (u64)((i64)keys[o] + ((i64)dy << 21) + ((i64)dz << 42) - 2);       // voxel at dx = -2
     const u64 b0 = k0 >> 3, b1 = (k0 + 4) >> 3;
@@ -108,14 +115,15 @@ __global__ void kmap_dense_kernel(const HashSlot *__restrict__ table, u32 mask, 
     for (int dx = 0; dx < 5; ++dx) {
         const u64 kk = k0 + dx;
         const i32 r = block_row((kk >> 3) == b0 ? e0 : e1, (u32)(kk & 7));
-        map[(i64)(line * 5 + dx) * n + o] = r;
+        map[(i64)(line * 5 + dx) * n + o] = abs(dx - 2) > half ? -1 : r;
     }
 }
 extern "C" int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n, int32_t *map,
-                              void *stream) {
+                              int kernel_size, void *stream) {
     if (n <= 0) return GPC_OK;
+    GPC_REQUIRE(kernel_size == 3 || kernel_size == 5, GPC_EINVAL, "kernel_size must be 3 or 5");
     dim3 grid(cdiv(n, 256), 25);
-    kmap_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>((const HashSlot *)table, (u32)(capacity - 1), keys, n, map);
+    kmap_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>((const HashSlot *)table, (u32)(capacity - 1), keys, n, map, kernel_size / 2);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }

@@ -110,9 +110,11 @@ int64_t gpc_hash_capacity(int64_t n);                      /* slots; table bytes
 int gpc_hash_build(const uint64_t *keys, int64_t n, void *table, int64_t capacity, void *stream);
 int gpc_hash_lookup(const void *table, int64_t capacity, const uint64_t *query, int64_t n,
                     int32_t *rows, void *stream);
-/* dense map, OFFSET-MAJOR: map[k*n + o] = row of (c_o + d_k) or -1; k = ((dz+2)*5+(dy+2))*5+(dx+2) */
+/* dense map, OFFSET-MAJOR: map[k*n + o] = row of (c_o + d_k) or -1; k = ((dz+2)*5+(dy+2))*5+(dx+2).  kernel_size = 5, or 3 (the
+ * reference CLI's default, compress_ue_4stage_conv.py:44): offsets outside the inner 3^3 are then absent, and a K = 3 conv runs
+ * on the K = 5 kernels with its 27 weight matrices placed at their K = 5 offset indices. */
 int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n,
-                   int32_t *map, void *stream);
+                   int32_t *map, int kernel_size, void *stream);
 /* tile pair lists for the conv: tiles of `tile_rows` consecutive output rows; for tile t and offset
  * k the pairs are [seg[t*126+k], seg[t*126+k+1]) (seg[t*126+125] == next tile's start);
  * pair_nbr = input row, pair_row = output row - t*tile_rows.  Two calls: count (fills seg as an

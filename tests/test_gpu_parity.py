@@ -413,13 +413,16 @@ def _encode_file(codec, xyz_t):
 @pytest.mark.parametrize("n,seed,ext", [(3000, 0, 16), (20000, 1, 16), (2500, 5, 12), (900, 7, 5), (100_000, 0, 16)])
 def test_codec_vs_oracle(env, n, seed, ext):
     """(100 000, seed 0) is BASELINE config[0]: the reference's own CPU-runnable case, full codec against the oracle."""
+    _check_codec_vs_oracle(env["codec"], env["w"], n, seed, ext)
+
+
+def _check_codec_vs_oracle(codec, w, n, seed, ext, K=5):
     from gauspcc_b200.synth import hac_like_cloud
     from oracle import oracle as O
-    codec, w = env["codec"], env["w"]
     xyz = hac_like_cloud(n, seed, extent_log2=ext)
     x = torch.tensor(xyz, dtype=torch.float32, device=codec.dev)
     blob, (bx, bo, streams), aux = _encode_file(codec, x)
-    ref_blob, ref = O.encode(xyz, w, collect=True)
+    ref_blob, ref = O.encode(xyz, w, K=K, collect=True)
     # pyramid / base / stream structure bit-exact
     assert np.array_equal(bx, ref["levels"][0][0]) and np.array_equal(bo, ref["levels"][0][1])
     assert len(streams) == 4 * len(ref["aux"])
@@ -439,7 +442,21 @@ def test_codec_vs_oracle(env, n, seed, ext):
     dec = codec.decode(bx, bo, streams).cpu().numpy()
     assert dec.dtype == np.float32
     assert np.array_equal(np.unique(dec.astype(np.int32), axis=0), np.unique(xyz, axis=0))
-    assert np.array_equal(dec, O.decode(ref_blob, w))
+    assert np.array_equal(dec, O.decode(ref_blob, w, K=K))
+
+
+@pytest.mark.parametrize("n,seed,ext", [(20000, 1, 16), (2500, 5, 12)])
+def test_codec_kernel_size_3_vs_oracle(env, n, seed, ext):
+    """kernel_size = 3 (the reference CLI default, compress_ue_4stage_conv.py:44): the 27 offsets run on the K = 5 kernels; same bars
+    against the oracle's K = 3 codec."""
+    from gauspcc_b200.codec import DeviceWeights, GausPcgcCodec
+    from gauspcc_b200.weights import make_synthetic_state_dict, state_dict_to_numpy
+    sd3 = make_synthetic_state_dict(kernel_size=3)
+    codec3 = GausPcgcCodec(DeviceWeights(sd3, env["dev"], kernel_size=3), env["dev"])
+    _check_codec_vs_oracle(codec3, state_dict_to_numpy(sd3), n, seed, ext, K=3)
+    um3 = GausPcgcCodec(codec3.w, env["dev"])                                # and with every level on the tcgen05 conv
+    um3.um_min_rows, um3.sparse_max_density = 1, 0.0
+    _check_codec_vs_oracle(um3, state_dict_to_numpy(sd3), n, seed, ext, K=3)
 
 
 @pytest.mark.parametrize("name", ["hac600", "blob", "hac2500"])
