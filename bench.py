@@ -159,18 +159,6 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- the repo arm
-def _pin_rank(local: int, world: int):
-    """cores / world CPUs per rank (contiguous slice of the affinity mask): 8 ranks x (16 range-coder threads + the launch thread) on
-    32 unpinned cores was what bent the end-to-end scaling curve in round 1"""
-    cpus = sorted(os.sched_getaffinity(0))
-    if world <= 1 or len(cpus) < 2 * world:
-        return len(cpus)
-    per = len(cpus) // world
-    mine = cpus[local * per:(local + 1) * per]
-    os.sched_setaffinity(0, mine)
-    return len(mine)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,7 +177,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    n_cpus = _pin_rank(local, world)                                 # before torch / the codec size their thread pools
+    from gauspcc_b200.shard import pin_rank
+    n_cpus = pin_rank(local, world)                                 # before torch / the codec size their thread pools
 
     import torch
     import torch.distributed as dist

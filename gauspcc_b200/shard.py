@@ -8,10 +8,21 @@ per-scene loop on 8 GPUs.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Sequence
 
-import torch
-import torch.distributed as dist
+
+def pin_rank(local_rank: int, world_size: int) -> int:
+    """Give this rank its own slice of the host CPUs (cores / world, contiguous in the affinity mask) and return its size.
+    Call it before the codec is created: the range-coder thread pool is sized from the affinity mask.  Eight unpinned ranks
+    x (16 coder threads + the launch thread) on one box's cores is what bent the end-to-end scaling curve in round 1."""
+    cpus = sorted(os.sched_getaffinity(0))
+    if world_size <= 1 or len(cpus) < 2 * world_size:
+        return len(cpus)
+    per = len(cpus) // world_size
+    mine = cpus[local_rank * per:(local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return len(mine)
 
 
 def assign_scenes(sizes: Sequence[int], world_size: int) -> List[List[int]]:
@@ -27,9 +38,11 @@ def assign_scenes(sizes: Sequence[int], world_size: int) -> List[List[int]]:
     return out
 
 
-def gather_results(local: torch.Tensor, n_scenes: int, assignment: List[List[int]]) -> torch.Tensor:
+def gather_results(local, n_scenes: int, assignment: List[List[int]]):
     """local: int64 [len(assignment[rank]), F] on this rank's device -> int64 [n_scenes, F] on every rank.
     Ragged shards are padded to the longest one so a single all_gather_into_tensor suffices."""
+    import torch
+    import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     F = local.shape[1]

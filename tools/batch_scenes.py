@@ -8,8 +8,10 @@ Each rank runs the public API (compress_point_cloud / decompress_point_cloud, ho
 {n_points, file_bytes, enc_us, dec_us} per scene.  Scene sizes are log-uniform in [100 K, 600 K].
 """
 import json, os, sys, tempfile, time
-import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gauspcc_b200.shard import pin_rank
+N_CPUS = pin_rank(int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)))      # before the codec sizes its coder threads
+import numpy as np, torch, torch.distributed as dist
 from gauspcc_b200 import pcc_utils, shard
 from gauspcc_b200.synth import hac_like_cloud
 from gauspcc_b200.weights import save_synthetic_checkpoint
@@ -45,7 +47,12 @@ def main():
     local_t = torch.tensor(rows, dtype=torch.int64, device=dev).reshape(-1, 4)
     res = shard.gather_results(local_t, n_scenes, assign)
     tmax = torch.tensor([t_local], dtype=torch.float64, device=dev)
-    if world > 1: dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tall = [torch.zeros_like(tmax) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(tall, tmax)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    else:
+        tall = [tmax]
     if rank == 0:
         r = res.cpu().numpy()
         assert (r[:, 0] == sizes).all()
@@ -53,7 +60,8 @@ def main():
                           "total_points": int(r[:, 0].sum()), "wall_s": round(float(tmax.item()), 3),
                           "Mpoints_s_e2e": round(float(r[:, 0].sum()) / float(tmax.item()) / 1e6, 3),
                           "mean_bpp": round(float((8 * r[:, 1] / r[:, 0]).mean()), 3), "lossless": True,
-                          "sum_enc_s": round(float(r[:, 2].sum()) / 1e6, 3), "sum_dec_s": round(float(r[:, 3].sum()) / 1e6, 3)}))
+                          "sum_enc_s": round(float(r[:, 2].sum()) / 1e6, 3), "sum_dec_s": round(float(r[:, 3].sum()) / 1e6, 3),
+                          "rank_wall_s": [round(float(t.item()), 3) for t in tall], "cpus_per_rank": N_CPUS}))
     if world > 1: dist.destroy_process_group()
 
 if __name__ == "__main__":
