@@ -81,6 +81,13 @@ SIGNATURES = {
     "gpc_ac_decode_begin_h": (c_int, [c_vp, c_vp, c_i64]),
     "gpc_ac_decode_more_h": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
     "gpc_ac_encode_lohi_h": (c_int, [c_vp, c_i64, c_vp, c_i64, C.POINTER(c_i64)]),
+    "gpc_attr_calculate_cdf": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    "gpc_attr_workspace_bytes": (c_sz, [c_i64, c_int]),
+    "gpc_attr_encode_table": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_attr_encode_gaussian": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_attr_merge_chunks": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "gpc_attr_decode_table": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_attr_decode_gaussian": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None

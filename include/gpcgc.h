@@ -245,6 +245,33 @@ int gpc_ac_decode_more_h(void *state_h, const uint16_t *cdf_h, int64_t n, int Lp
 /* same bitstream as gpc_ac_encode_h, fed with the (c_low, c_high) words of gpc_head_cdf_sym */
 int gpc_ac_encode_lohi_h(const uint32_t *lohi_h, int64_t n, uint8_t *out_h, int64_t cap, int64_t *out_len_h);
 
+/* ---- f-4: HAC's chunked attribute coder (HAC/submodules/arithmetic.zip!arithmetic/arithmetic_kernel.cu; binding
+ * arithmetic.cpp:4-49; callers HAC/utils/encodings_cuda.py:317-432).  All pointers are DEVICE pointers.  A chunk of
+ * `chunk_size` symbols (10 000 in encodings_cuda.py:6) is one serial 32-bit range coder, as in the reference. ---- */
+/* arithmetic.calculate_cdf (arithmetic_kernel.cu:11-55): lower[n][Lp], Lp = max_value - min_value + 2 */
+int gpc_attr_calculate_cdf(const float *mean, const float *scale, const float *Q, int64_t n, int min_value,
+                           int max_value, float *lower, void *stream);
+size_t gpc_attr_workspace_bytes(int64_t n, int chunk_size);
+/* arithmetic.arithmetic_encode (:94-163, :186-232), first half: per-chunk streams into the workspace, cnt[chunks] = bytes per
+ * chunk (the reference's out_cnt_all), offsets[chunks + 1] = their exclusive prefix sums (offsets[chunks] = total bytes).
+ * Synchronises the stream once (status word).  Symbols outside [0, Lp - 2] are an error. */
+int gpc_attr_encode_table(const int16_t *sym, const float *cdf, int64_t n, int Lp, int chunk_size, int32_t *cnt,
+                          uint32_t *offsets, void *ws, size_t ws_bytes, void *stream);
+/* the same with the Gaussian CDF evaluated for the two bin edges of each symbol instead of read from a table:
+ * calculate_cdf + arithmetic_encode of encoder_gaussian (encodings_cuda.py:335-373) without lower[n][Lp] */
+int gpc_attr_encode_gaussian(const int16_t *sym, const float *mean, const float *scale, const float *Q, int64_t n,
+                             int min_value, int max_value, int chunk_size, int32_t *cnt, uint32_t *offsets, void *ws,
+                             size_t ws_bytes, void *stream);
+/* second half (merge_chunks_kernel, :166-183): out[offsets[chunks]] = the chunks' bytes back to back */
+int gpc_attr_merge_chunks(const void *ws, int64_t n, int chunk_size, const uint32_t *offsets, uint8_t *out, void *stream);
+/* arithmetic.arithmetic_decode (:290-356, :365-407) */
+int gpc_attr_decode_table(const float *cdf, const uint8_t *in, const int32_t *cnt, int64_t n, int Lp, int chunk_size,
+                          int16_t *sym, void *ws, size_t ws_bytes, void *stream);
+/* calculate_cdf + arithmetic_decode of decoder_gaussian (encodings_cuda.py:394-432) without the table */
+int gpc_attr_decode_gaussian(const float *mean, const float *scale, const float *Q, const uint8_t *in, const int32_t *cnt,
+                             int64_t n, int min_value, int max_value, int chunk_size, int16_t *sym, void *ws,
+                             size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,6 +163,48 @@ def ac_decode(cdf: np.ndarray, stream: bytes) -> np.ndarray:
     return sym
 
 
+# ----------------------------------------------------------------------------- HAC attribute coder
+# HAC/submodules/arithmetic.zip!arithmetic/arithmetic_kernel.cu restated on top of the range coder above: the reference codes
+# chunk c (symbols [c * chunk_size, (c + 1) * chunk_size)) with its own coder (:94-163) whose integer CDF entries are
+# c = rn(cdf_float * (2^16 - (Lp - 1))) + index (:121-122; binsearch :264-287 compares the same values as uint16).
+def attr_cdf(mean, scale, Q, min_value: int, max_value: int) -> np.ndarray:
+    """calculate_cdf_kernel (:7-28).  erfc is evaluated in double and rounded to float32: CUDA's float erfc differs from it in
+    the last bits, so byte-exact comparisons feed attr_encode / attr_decode the table the GPU produced."""
+    from math import sqrt
+    from scipy.special import erfc
+    mean = np.asarray(mean, np.float32)
+    Q = np.asarray(Q, np.float32)
+    sc = np.maximum(np.asarray(scale, np.float32).astype(np.float64), 1e-9).astype(np.float32)
+    i = np.arange(max_value - min_value + 2)
+    sample = ((min_value + i - 0.5)[None, :] * Q.astype(np.float64)[:, None]).astype(np.float32)
+    arg = (-(sample - mean[:, None]) / (sc * np.float32(sqrt(2.0)))[:, None]).astype(np.float32)
+    return (0.5 * erfc(arg.astype(np.float64))).astype(np.float32)
+
+
+def _attr_int_rows(cdf: np.ndarray) -> np.ndarray:
+    n, Lp = cdf.shape
+    v = np.rint(cdf.astype(np.float32) * np.float32(65536 - (Lp - 1))).astype(np.int64) + np.arange(Lp)
+    return (v & 0xFFFF).astype(np.uint16)
+
+
+def attr_encode(sym: np.ndarray, cdf: np.ndarray, chunk_size: int):
+    """arithmetic_encode_cu (:186-232) -> (stream bytes, bytes per chunk int32[chunks])"""
+    rows = _attr_int_rows(np.asarray(cdf, np.float32))
+    sym = np.asarray(sym, np.int16)
+    parts = [ac_encode(rows[o:o + chunk_size], sym[o:o + chunk_size]) for o in range(0, len(sym), chunk_size)]
+    return b"".join(parts), np.array([len(p) for p in parts], dtype=np.int32)
+
+
+def attr_decode(cdf: np.ndarray, stream: bytes, cnt: np.ndarray, chunk_size: int) -> np.ndarray:
+    """arithmetic_decode_cu (:365-407)"""
+    rows = _attr_int_rows(np.asarray(cdf, np.float32))
+    out, pos = [], 0
+    for c, o in enumerate(range(0, rows.shape[0], chunk_size)):
+        out.append(ac_decode(rows[o:o + chunk_size], stream[pos:pos + int(cnt[c])]))
+        pos += int(cnt[c])
+    return np.concatenate(out) if out else np.zeros(0, np.int16)
+
+
 # container -- kit/op.py:32-48
 def pack_byte_stream_ls(streams: List[bytes]) -> bytes:
     out = np.array(len(streams), dtype=np.uint16).tobytes()

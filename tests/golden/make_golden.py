@@ -219,6 +219,9 @@ def _force_cpu_factories():
         setattr(torch, name, wrapped)
 
 
+BIG_N, BIG_SEED, BIG_EVERY = 60_000, 21, 128
+
+
 def main():
     from gauspcc_b200.synth import hac_like_cloud
     from gauspcc_b200.weights import make_synthetic_state_dict
@@ -304,8 +307,39 @@ def main():
             out[f"{name}_nprob"] = np.array([p.shape[0] for p in enc_probs])
             out[f"{name}_probs"] = np.concatenate([p.reshape(-1) for p in enc_probs])
         print(name, xyz.shape, "bytes", len(blob), "bpp %.3f" % r["bpp"], "streams", len(enc_probs))
-    torch.nn.Softmax.forward = orig_softmax
     np.savez_compressed(os.path.join(HERE, "codec_golden.npz"), **out)
+
+    # ---- 3. one cloud of realistic size (60 K anchors, 11 coded levels) through the same reference driver.  The fixture keeps what
+    # is size-independent or small: stream lengths, base level, hashes of the cloud / the decoded rows, and every 128th
+    # row of every probability tensor (the cloud itself is regenerated from its seed and checked against the hash).
+    import hashlib
+    from gauspcc_b200 import bitstream
+    xyz = hac_like_cloud(BIG_N, BIG_SEED)
+    probs.clear()
+    order = pcc_utils.calculate_morton_order(torch.tensor(xyz.astype(np.float32)))
+    xyz_sorted = torch.tensor(xyz.astype(np.float32))[order]
+    binp = os.path.join(tmp, "big", "xyz_pcc.bin")
+    r = pcc_utils.compress_point_cloud(xyz_sorted, ckpt, binp)
+    enc_probs = [p.copy() for p in probs]
+    probs.clear()
+    d = pcc_utils.decompress_point_cloud(binp, ckpt)
+    for a, b in zip(enc_probs, probs):
+        assert np.array_equal(a, b)
+    dec = d["point_cloud"].numpy()
+    assert np.array_equal(np.unique(dec.astype(np.int32), axis=0), np.unique(xyz, axis=0))
+    blob = open(binp, "rb").read()
+    _, bx, bo, streams = bitstream.read_file(blob)
+    np.savez_compressed(os.path.join(HERE, "codec_golden_60k.npz"),
+                        n=np.array([BIG_N]), seed=np.array([BIG_SEED]),
+                        xyz_sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(xyz.astype(np.int32)).tobytes()).digest(), dtype=np.uint8),
+                        decoded_sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(dec.astype(np.int32)).tobytes()).digest(), dtype=np.uint8),
+                        file_bytes=np.array([len(blob)]), stream_lens=np.array([len(s) for s in streams]),
+                        base_xyz=bx, base_occ=bo,
+                        nprob=np.array([p.shape[0] for p in enc_probs]), prob_cols=np.array([p.shape[1] for p in enc_probs]),
+                        probs_every=np.array([BIG_EVERY]),
+                        probs=np.concatenate([p[::BIG_EVERY].reshape(-1) for p in enc_probs]))
+    print("big", xyz.shape, "bytes", len(blob), "bpp %.3f" % r["bpp"], "streams", len(enc_probs))
+    torch.nn.Softmax.forward = orig_softmax
     print("wrote", os.listdir(HERE))
 
 
