@@ -77,8 +77,7 @@ def test_python_boundary_matches_reference_names():
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def ref_ext():
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import build_ref_arithmetic
+    from oracle import build_ref_arithmetic
     return build_ref_arithmetic.load_module()                               # None when the reference was not present at build time
 
 

@@ -478,6 +478,27 @@ def test_codec_vs_reference_golden(env, golden_dir, name):
     assert np.array_equal(dec, cg[f"{name}_decoded"])                    # same rows, same order as the reference run
 
 
+def test_codec_vs_reference_golden_60k(env, golden_dir):
+    """The 60 K-anchor fixture of the reference's own driver (make_golden.py section 3) against the CUDA codec: base level, stream
+    sizes within 0.5 %, every 128th row of every probability tensor within 1e-3, decoded rows identical in the reference's order."""
+    import hashlib
+    from gauspcc_b200.synth import hac_like_cloud
+    codec = env["codec"]
+    g = np.load(os.path.join(golden_dir, "codec_golden_60k.npz"))
+    xyz = hac_like_cloud(int(g["n"][0]), int(g["seed"][0]))
+    assert hashlib.sha256(np.ascontiguousarray(xyz.astype(np.int32)).tobytes()).digest() == g["xyz_sha256"].tobytes()
+    blob, (bx, bo, streams), aux = _encode_file(codec, torch.tensor(xyz, dtype=torch.int32, device=codec.dev))
+    assert np.array_equal(bx, g["base_xyz"]) and np.array_equal(bo, g["base_occ"]) and len(streams) == len(g["stream_lens"])
+    assert abs(len(blob) - int(g["file_bytes"][0])) <= SIZE_TOL * int(g["file_bytes"][0])
+    assert all(abs(len(a) - int(b)) <= max(4, SIZE_TOL * int(b)) for a, b in zip(streams, g["stream_lens"]))
+    every = int(g["probs_every"][0])
+    assert [p.shape[0] for p in aux["probs"]] == list(g["nprob"])
+    got = np.concatenate([p[::every].cpu().numpy().reshape(-1) for p in aux["probs"]])
+    assert np.abs(got - g["probs"]).max() <= PROB_TOL
+    dec = codec.decode(bx, bo, streams).cpu().numpy()
+    assert hashlib.sha256(np.ascontiguousarray(dec.astype(np.int32)).tobytes()).digest() == g["decoded_sha256"].tobytes()
+
+
 def test_edge_cases(env):
     codec = env["codec"]
     dev = codec.dev

@@ -132,6 +132,37 @@ def test_codec_vs_reference_driver(cg, weights_np, name):
     assert k == len(st_r)
 
 
+def _golden_60k(golden_dir):
+    import hashlib
+    from gauspcc_b200.synth import hac_like_cloud
+    g = np.load(os.path.join(golden_dir, "codec_golden_60k.npz"))
+    xyz = hac_like_cloud(int(g["n"][0]), int(g["seed"][0]))
+    assert hashlib.sha256(np.ascontiguousarray(xyz.astype(np.int32)).tobytes()).digest() == g["xyz_sha256"].tobytes(), \
+        "synth.hac_like_cloud changed: regenerate tests/golden (make_golden.py)"
+    return g, xyz
+
+
+def test_codec_vs_reference_driver_60k(golden_dir, weights_np):
+    """A cloud of realistic size (60 K anchors, 11 coded levels, 528 KB of stream) through the reference's own driver
+    (make_golden.py section 3): stream sizes, base level, sampled probabilities and the decoded rows."""
+    import hashlib
+    g, xyz = _golden_60k(golden_dir)
+    blob, info = O.encode(xyz, weights_np, collect=True)
+    _, bc, bo, st = _split_file(blob)
+    assert np.array_equal(bc, g["base_xyz"]) and np.array_equal(bo, g["base_occ"])
+    ref_lens = g["stream_lens"]
+    assert len(st) == len(ref_lens)
+    assert abs(len(blob) - int(g["file_bytes"][0])) <= 0.002 * int(g["file_bytes"][0])
+    assert all(abs(len(a) - int(b)) <= max(2, 0.002 * int(b)) for a, b in zip(st, ref_lens))
+    every = int(g["probs_every"][0])
+    probs = [p for lv in info["aux"] for p in lv["probs"]]
+    assert [p.shape[0] for p in probs] == list(g["nprob"]) and [p.shape[1] for p in probs] == list(g["prob_cols"])
+    got = np.concatenate([p[::every].reshape(-1) for p in probs])
+    assert np.abs(got - g["probs"]).max() < 2e-4
+    dec = O.decode(blob, weights_np)
+    assert hashlib.sha256(np.ascontiguousarray(dec.astype(np.int32)).tobytes()).digest() == g["decoded_sha256"].tobytes()
+
+
 def test_roundtrip_signed_and_tiny(weights_np):
     rng = np.random.default_rng(3)
     for xyz in (rng.integers(-50, 50, size=(40, 3)).astype(np.int32),          # < 64 points: base only

@@ -14,7 +14,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from gauspcc_b200 import arithmetic as A
 
 CHUNK = 10000
@@ -64,7 +63,7 @@ def main():
             "ours_fused": {"enc_ms": round(t_enc, 3), "dec_ms": round(t_dec, 3),
                            "enc_Msym_s": round(n / t_enc / 1e3, 1), "dec_Msym_s": round(n / t_dec / 1e3, 1)},
             "ours_table": {"enc_ms": round(t_enc_t, 3), "dec_ms": round(t_dec_t, 3)}}
-    import build_ref_arithmetic
+    from oracle import build_ref_arithmetic
     ref = build_ref_arithmetic.load_module()
     if ref is None:
         line["reference"] = "oracle/_ref/arithmetic.so not built"
