@@ -47,7 +47,7 @@ SIGNATURES = {
     "gpc_hash_capacity": (c_i64, [c_i64]),
     "gpc_hash_build": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gpc_hash_lookup": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
-    "gpc_kmap_dense": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_vp]),
+    "gpc_kmap_dense": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp]),
     "gpc_kmap_pairs_workspace_bytes": (c_sz, [c_i64, c_int]),
     "gpc_kmap_pairs_count": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gpc_kmap_pairs_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
@@ -65,6 +65,7 @@ SIGNATURES = {
     "gpc_debug_conv_um_profile": (c_int, [c_vp, c_int]),
     "gpc_kmap_um_workspace_bytes": (c_sz, [c_i64, c_int]),
     "gpc_kmap_um_count": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gpc_kmap_um_scan": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gpc_kmap_um_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gpc_spconv_pack_weights_um": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "gpc_spconv_fwd_um": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),

@@ -290,7 +290,7 @@ class GausPcgcCodec:
 
     # ------------------------------------------------------------------ kernel map / conv
     def _v6_config(self, n: int) -> Tuple[int, int]:
-        """(rows per CTA, kernel variant) of the mma.sync conv for a level of n rows (tools/conv_ab.py):
+        """(rows per CTA, kernel variant) of the mma.sync conv for a level of n rows:
         128 / 64 rows per warp on big levels (W^T reuse, v6d); fewer rows on the coarse levels so that they still fill the 148 SMs;
         on the coarse levels the 125 offsets of a tile are additionally split over 8 / 16 warps (variants 46 / 47): those
         launches are bound by one warp's chain of dependent 8-pair tiles, ~63 us each before, 15-30 us now."""
@@ -362,39 +362,58 @@ class GausPcgcCodec:
         """hash build n*12 + cap*12 (cap = 2n), probes n*K^3*8; the pair stream adds pairs*12 (not known here)"""
         return n * 12 + 2 * n * 12 + n * 125 * 8
 
-    def dense_map(self, keys: torch.Tensor) -> torch.Tensor:
-        """hash table of the level + the offset-major [125][n] map of input rows (-1 = absent)"""
+    def dense_map(self, keys: torch.Tensor, count_tile: int = 0):
+        """hash table of the level + the offset-major [125][n] map of input rows (-1 = absent); with count_tile also the number of
+        present neighbours per (tile of count_tile rows, offset), counted from the probes: returns (map, cell_counts)"""
         n = keys.shape[0]
         cap = self.lib.gpc_hash_capacity(n)
         table = self._ws(cap * 16)
         self._call("gpc_hash_build", _ptr(keys), n, _ptr(table), cap, self._stream())
         dense = self._empty((125, n), torch.int32)
-        self._call("gpc_kmap_dense", _ptr(table), cap, _ptr(keys), n, _ptr(dense), self.w.kernel_size, self._stream())
-        return dense
+        cells = self._empty((((n + count_tile - 1) // count_tile) * 126,), torch.int32) if count_tile else None
+        self._call("gpc_kmap_dense", _ptr(table), cap, _ptr(keys), n, _ptr(dense), self.w.kernel_size, count_tile, _ptr(cells),
+                   self._stream())
+        return (dense, cells) if count_tile else dense
+
+    def _scan_um(self, cells: torch.Tensor, n: int, tr: int):
+        """_count_um from the cell counts the dense-map kernel produced"""
+        seg = self._empty((((n + tr - 1) // tr) * 126 + 1,), torch.int32)
+        tot = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        ws_b = self.lib.gpc_kmap_um_workspace_bytes(n, tr)
+        ws = self._ws(ws_b)
+        self._call("gpc_kmap_um_scan", _ptr(cells), n, tr, _ptr(seg), _ptr(tot), _ptr(ws), ws_b, self._stream())
+        n_pairs, n_real = (int(v) for v in tot.tolist())
+        return seg, n_pairs, n_real
 
     def build_kmap(self, keys: torch.Tensor, family: Optional[str] = None) -> KMap:
         """Kernel map of a coordinate set in the form of the conv kernel the level runs.  The family is a function of the level only
         (rows, pairs per row -- see __init__); `family` ("v6" | "um" | "sparse") forces one (tests / tools, both directions alike)."""
         n = keys.shape[0]
-        dense = self.dense_map(keys)
         big = n >= min(self.um_min_rows, self.sparse_min_rows)
         if family is None and not big:
             family = "v6"
         if family == "v6":
             tr, v6v = self._v6_config(n)
-            return self._v6_map(dense, n, tr, v6v)
+            return self._v6_map(self.dense_map(keys), n, tr, v6v)
         if family == "sparse":
-            return self._sparse_map(dense, n)
-        # big level: one count with the tcgen05 tiling tells the density (pairs per row, centre included)
-        counted = self._count_um(dense, n, self.um_tile_rows)
+            return self._sparse_map(self.dense_map(keys), n)
+        # big level: the probes count the pairs per (tile of the tcgen05 conv, offset): density (pairs per row, centre included) and
+        # the first pass of the pair stream in one
+        tr = self.um_tile_rows
+        if tr >= 256:
+            dense, cells = self.dense_map(keys, tr)
+            counted = self._scan_um(cells, n, tr)
+        else:
+            dense = self.dense_map(keys)
+            counted = self._count_um(dense, n, tr)
         density = counted[2] / max(n, 1)
         if family is None:
             if n >= self.sparse_min_rows and 0 < self.sparse_max_density and density < self.sparse_max_density and n < 30_000_000:
                 return self._sparse_map(dense, n)            # 32-bit straggler indices: n * 124 < 2^32
             if n < self.um_min_rows:
-                tr, v6v = self._v6_config(n)
-                return self._v6_map(dense, n, tr, v6v)
-        return self._um_map(dense, n, self.um_tile_rows, counted)
+                tr6, v6v = self._v6_config(n)
+                return self._v6_map(dense, n, tr6, v6v)
+        return self._um_map(dense, n, tr, counted)
 
     def split_rows(self, x: torch.Tensor) -> torch.Tensor:
         """fp32 rows [n,32] -> split rows (int32 [n,32]: 16 words of bf16x2 hi | 16 words of bf16x2 lo)."""

@@ -95,35 +95,66 @@ extern "C" int gpc_hash_lookup(const void *table, int64_t capacity, const uint64
 // one thread per (row o, line (dz,dy)); blockIdx.y = line, so every one of the 5 output planes is written coalesced.
 // half = kernel_size / 2: offsets with a component beyond it are absent (-1) without a probe -- a K = 3 conv
 // (compress_ue_4stage_conv.py:44) runs on the K = 5 machinery with its 27 offsets at their K = 5 indices.
-__global__ void kmap_dense_kernel(const HashSlot *__restrict__ table, u32 mask, const u64 *__restrict__ keys, i64 n,
-                                  i32 *__restrict__ map, int half) {
+// cell_counts (optional): number of present neighbours per (tile of tile_rows rows, offset), [tiles][126] -- the first pass of the
+// tcgen05 conv's pair stream and the level's density fall out of the probes instead of a second read of the 500 B-per-row map.
+__global__ void __launch_bounds__(256) kmap_dense_kernel(const HashSlot *__restrict__ table, u32 mask, const u64 *__restrict__ keys,
+                                                        i64 n, i32 *__restrict__ map, int half, int tile_rows,
+                                                        u32 *__restrict__ cell_counts) {
+    __shared__ u32 cnt[2][5];                          // a block of 256 rows touches at most two tiles (tile_rows >= 256)
     const int line = blockIdx.y;                      // (dz+2)*5 + (dy+2)
-    i64 o = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= n) return;
-    const int dy = line % 5 - 2, dz = line / 5 - 2;
-    if (abs(dy) > half || abs(dz) > half) {
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) map[(i64)(line * 5 + dx) * n + o] = -1;
-        return;
+    const i64 b0row = (i64)blockIdx.x * blockDim.x;
+    const i64 o = b0row + threadIdx.x;
+    if (cell_counts) {
+        if (threadIdx.x < 10) cnt[threadIdx.x / 5][threadIdx.x % 5] = 0;
+        __syncthreads();
     }
-    // fields never under/overflow: |c| <= 2^20 - 16
-    const u64 k0 = (u64)((i64)keys[o] + ((i64)dy << 21) + ((i64)dz << 42) - 2);       // voxel at dx = -2
-    const u64 b0 = k0 >> 3, b1 = (k0 + 4) >> 3;
-    const uint2 e0 = hash_find_block(table, mask, b0);
-    const uint2 e1 = b1 != b0 ? hash_find_block(table, mask, b1) : e0;
+    const int dy = line % 5 - 2, dz = line / 5 - 2;
+    i32 r[5] = {-1, -1, -1, -1, -1};
+    if (o < n && abs(dy) <= half && abs(dz) <= half) {
+        // fields never under/overflow: |c| <= 2^20 - 16
+        const u64 k0 = (u64)((i64)keys[o] + ((i64)dy << 21) + ((i64)dz << 42) - 2);       // voxel at dx = -2
+        const u64 b0 = k0 >> 3, b1 = (k0 + 4) >> 3;
+        const uint2 e0 = hash_find_block(table, mask, b0);
+        const uint2 e1 = b1 != b0 ? hash_find_block(table, mask, b1) : e0;
 #pragma unroll
-    for (int dx = 0; dx < 5; ++dx) {
-        const u64 kk = k0 + dx;
-        const i32 r = block_row((kk >> 3) == b0 ? e0 : e1, (u32)(kk & 7));
-        map[(i64)(line * 5 + dx) * n + o] = abs(dx - 2) > half ? -1 : r;
+        for (int dx = 0; dx < 5; ++dx) {
+            const u64 kk = k0 + dx;
+            const i32 v = block_row((kk >> 3) == b0 ? e0 : e1, (u32)(kk & 7));
+            r[dx] = abs(dx - 2) > half ? -1 : v;
+        }
+    }
+    if (o < n) {
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) map[(i64)(line * 5 + dx) * n + o] = r[dx];
+    }
+    if (cell_counts) {
+        const i64 t0 = b0row / tile_rows;
+        const int tw = (int)((b0row + (threadIdx.x & ~31)) / tile_rows - t0);              // the warp's 32 rows lie in one tile
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const u32 c = __popc(__ballot_sync(0xFFFFFFFFu, r[dx] >= 0));
+            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[tw][dx], c);
+        }
+        __syncthreads();
+        if (threadIdx.x < 10) {
+            const u32 c = cnt[threadIdx.x / 5][threadIdx.x % 5];
+            if (c) atomicAdd(&cell_counts[(t0 + threadIdx.x / 5) * (GPC_K3 + 1) + line * 5 + threadIdx.x % 5], c);
+        }
     }
 }
 extern "C" int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n, int32_t *map,
-                              int kernel_size, void *stream) {
+                              int kernel_size, int tile_rows, uint32_t *cell_counts, void *stream) {
     if (n <= 0) return GPC_OK;
     GPC_REQUIRE(kernel_size == 3 || kernel_size == 5, GPC_EINVAL, "kernel_size must be 3 or 5");
+    cudaStream_t st = as_stream(stream);
+    if (cell_counts) {
+        GPC_REQUIRE(tile_rows >= 256 && tile_rows % 32 == 0, GPC_EINVAL, "counting needs tile_rows >= 256, a multiple of 32");
+        const i64 tiles = (n + tile_rows - 1) / tile_rows;
+        GPC_CUDA_CHECK(cudaMemsetAsync(cell_counts, 0, (size_t)tiles * (GPC_K3 + 1) * 4, st));
+    }
     dim3 grid(cdiv(n, 256), 25);
-    kmap_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>((const HashSlot *)table, (u32)(capacity - 1), keys, n, map, kernel_size / 2);
+    kmap_dense_kernel<<<grid, 256, 0, st>>>((const HashSlot *)table, (u32)(capacity - 1), keys, n, map, kernel_size / 2,
+                                            cell_counts ? tile_rows : 256, cell_counts);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
@@ -343,7 +374,7 @@ extern "C" int gpc_kmap_pairs_fill(const int32_t *map, int64_t n, int tile_rows,
 // per entry, the input row (padding: 0xFFFFFFFF = out of bounds for the gather) and the BYTE OFFSET of the pair's accumulator row
 // inside the tile (row * 128; padding: the dummy row tile_rows * 128).
 __global__ void __launch_bounds__(128) kmap_um_count_kernel(const i32 *__restrict__ map, i64 n, int tile_rows, i64 cells,
-                                                           u32 *__restrict__ counts, unsigned long long *__restrict__ n_real) {
+                                                           u32 *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const i64 cell = (i64)blockIdx.x * 4 + (threadIdx.x >> 5);           // = tile * 126 + k; k == 125 is the zero pad of the scan
     if (cell >= cells) return;
@@ -357,11 +388,26 @@ __global__ void __launch_bounds__(128) kmap_um_count_kernel(const i32 *__restric
         for (int r = lane; r < rows; r += 32) c += m[r] >= 0;
         c = __reduce_add_sync(0xFFFFFFFFu, c);
     }
-    if (lane == 0) {
-        counts[cell] = (c + 15u) & ~15u;
-        if (c) atomicAdd(n_real, (unsigned long long)c);
+    if (lane == 0) counts[cell] = c;
+}
+// true pairs of the level = sum of the raw cell counts
+__global__ void __launch_bounds__(256) kmap_um_total_kernel(const u32 *__restrict__ counts, i64 cells, unsigned long long *n_real) {
+    __shared__ unsigned long long part[8];
+    unsigned long long s = 0;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < cells; i += (i64)gridDim.x * 256) s += counts[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) s += part[w];
+        if (s) atomicAdd(n_real, s);
     }
 }
+struct Pad16Load {                                                       // every non-empty cell padded to a multiple of 16 entries
+    const u32 *p;
+    __device__ u32 operator()(i64 i) const { return (p[i] + 15u) & ~15u; }
+};
 __global__ void __launch_bounds__(128) kmap_um_fill_kernel(const i32 *__restrict__ map, i64 n, int tile_rows, i64 cells,
                                                           const u32 *__restrict__ seg, u32 *__restrict__ pair_nbr, u32 *__restrict__ pair_off) {
     const int lane = threadIdx.x & 31;
@@ -394,9 +440,9 @@ __global__ void __launch_bounds__(128) kmap_um_fill_kernel(const i32 *__restrict
     }
 }
 extern "C" size_t gpc_kmap_um_workspace_bytes(int64_t n, int tile_rows) { return gpc_kmap_pairs_workspace_bytes(n, tile_rows); }
-// totals: device u64[2] = {stream entries (padded), true pairs}
-extern "C" int gpc_kmap_um_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals, void *ws,
-                                 size_t ws_bytes, void *stream) {
+// totals: device u64[2] = {stream entries (padded), true pairs}.  cell_counts: what gpc_kmap_dense counted with the same tile_rows.
+extern "C" int gpc_kmap_um_scan(const uint32_t *cell_counts, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals,
+                                void *ws, size_t ws_bytes, void *stream) {
     cudaStream_t st = as_stream(stream);
     GPC_REQUIRE(tile_rows >= 32 && tile_rows <= 1024, GPC_EINVAL, "tile_rows must be in 32..1024");
     GPC_CUDA_CHECK(cudaMemsetAsync(totals, 0, 16, st));
@@ -404,15 +450,28 @@ extern "C" int gpc_kmap_um_count(const int32_t *map, int64_t n, int tile_rows, u
     GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_um_workspace_bytes(n, tile_rows), GPC_ENOSPC, "workspace too small");
     const i64 tiles = (n + tile_rows - 1) / tile_rows;
     const i64 m = tiles * (GPC_K3 + 1);
-    u32 *counts = (u32 *)ws;
     void *scan_ws = (char *)ws + align_up((size_t)m * 4, 256);
-    kmap_um_count_kernel<<<cdiv(m, 4), 128, 0, st>>>(map, n, tile_rows, m, counts, totals + 1);
+    kmap_um_total_kernel<<<(unsigned)min((i64)296, (m + 255) / 256), 256, 0, st>>>(cell_counts, m, totals + 1);
     GPC_LAUNCH_CHECK();
-    PtrLoad<u32> pl{counts};
-    int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, m, seg, scan_ws, st);      // seg has m + 1 entries
+    Pad16Load pl{cell_counts};
+    int rc = device_exclusive_scan<u32, Pad16Load>(pl, m, seg, scan_ws, st);         // seg has m + 1 entries
     if (rc) return rc;
     GPC_CUDA_CHECK(cudaMemcpyAsync(totals, seg + m, 4, cudaMemcpyDeviceToDevice, st));
     return GPC_OK;
+}
+// the same from a dense map that was built without counting (any tile_rows in 32..1024; tools, tests)
+extern "C" int gpc_kmap_um_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals, void *ws,
+                                 size_t ws_bytes, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    GPC_REQUIRE(tile_rows >= 32 && tile_rows <= 1024, GPC_EINVAL, "tile_rows must be in 32..1024");
+    if (n <= 0) { GPC_CUDA_CHECK(cudaMemsetAsync(totals, 0, 16, st)); return GPC_OK; }
+    GPC_REQUIRE(ws && ws_bytes >= gpc_kmap_um_workspace_bytes(n, tile_rows), GPC_ENOSPC, "workspace too small");
+    const i64 tiles = (n + tile_rows - 1) / tile_rows;
+    const i64 m = tiles * (GPC_K3 + 1);
+    u32 *counts = (u32 *)ws;
+    kmap_um_count_kernel<<<cdiv(m, 4), 128, 0, st>>>(map, n, tile_rows, m, counts);
+    GPC_LAUNCH_CHECK();
+    return gpc_kmap_um_scan(counts, n, tile_rows, seg, totals, ws, ws_bytes, stream);
 }
 extern "C" int gpc_kmap_um_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr,
                                 uint32_t *pair_off, void *stream) {

@@ -112,9 +112,12 @@ int gpc_hash_lookup(const void *table, int64_t capacity, const uint64_t *query, 
                     int32_t *rows, void *stream);
 /* dense map, OFFSET-MAJOR: map[k*n + o] = row of (c_o + d_k) or -1; k = ((dz+2)*5+(dy+2))*5+(dx+2).  kernel_size = 5, or 3 (the
  * reference CLI's default, compress_ue_4stage_conv.py:44): offsets outside the inner 3^3 are then absent, and a K = 3 conv runs
- * on the K = 5 kernels with its 27 weight matrices placed at their K = 5 offset indices. */
+ * on the K = 5 kernels with its 27 weight matrices placed at their K = 5 offset indices.
+ * cell_counts (optional, may be NULL): u32[tiles * 126], tiles = ceil(n / tile_rows), tile_rows >= 256 and a multiple of 32:
+ * the number of present neighbours per (tile, offset), counted from the probes themselves (zeroed by the call) -- the first
+ * pass of gpc_kmap_um_scan and the level's density (true pairs per row) without a second read of the map. */
 int gpc_kmap_dense(const void *table, int64_t capacity, const uint64_t *keys, int64_t n,
-                   int32_t *map, int kernel_size, void *stream);
+                   int32_t *map, int kernel_size, int tile_rows, uint32_t *cell_counts, void *stream);
 /* tile pair lists for the conv: tiles of `tile_rows` consecutive output rows; for tile t and offset
  * k the pairs are [seg[t*126+k], seg[t*126+k+1]) (seg[t*126+125] == next tile's start);
  * pair_nbr = input row, pair_row = output row - t*tile_rows.  Two calls: count (fills seg as an
@@ -198,6 +201,9 @@ int gpc_spconv_pack_weights_um(const float *W, int n_kernels, void *Wp, void *st
 size_t gpc_kmap_um_workspace_bytes(int64_t n, int tile_rows);
 int gpc_kmap_um_count(const int32_t *map, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals, void *ws,
                       size_t ws_bytes, void *stream);
+/* the same from the cell counts gpc_kmap_dense produced with this tile_rows (no pass over the map) */
+int gpc_kmap_um_scan(const uint32_t *cell_counts, int64_t n, int tile_rows, uint32_t *seg, unsigned long long *totals, void *ws,
+                     size_t ws_bytes, void *stream);
 int gpc_kmap_um_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr, uint32_t *pair_off,
                      void *stream);
 int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr, const uint32_t *pair_off,

@@ -162,6 +162,18 @@ def test_kernel_map(env, n, seed, ext):
     assert n_pairs == n_real == int((ref >= 0).sum()) == seg[-1]
     # the conv's own map counts the same pairs
     assert codec.build_kmap(keys).n_real == n_real
+    # counts taken from the probes (per (tile, offset) cell) == counts of the map, for tile heights that do / do not divide a block
+    for ctile in (256, 384):
+        dense2, cells = codec.dense_map(keys, ctile)
+        assert torch.equal(dense2, dense)
+        tiles = (n + ctile - 1) // ctile
+        pad = np.full((tiles * ctile, 125), -1, dtype=ref.dtype)
+        pad[:n] = ref
+        want = (pad.reshape(tiles, ctile, 125) >= 0).sum(1)
+        got = cells.cpu().numpy().reshape(tiles, 126)
+        assert np.array_equal(got[:, :125], want) and not got[:, 125].any()
+        a, b = codec._scan_um(cells, n, ctile), codec._count_um(dense, n, ctile)
+        assert torch.equal(a[0], b[0]) and a[1:] == b[1:] and a[2] == n_real
     for t in range((n + tr - 1) // tr):
         sub = ref[t * tr:(t + 1) * tr]
         for k in (0, 31, 62, 63, 124):
