@@ -68,7 +68,7 @@ SIGNATURES = {
     "gpc_kmap_um_scan": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gpc_kmap_um_fill": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gpc_spconv_pack_weights_um": (c_int, [c_vp, c_int, c_vp, c_vp]),
-    "gpc_spconv_fwd_um": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "gpc_spconv_fwd_um": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "gpc_embed_rows": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "gpc_gather_parent_add_octant": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "gpc_add_ctx_embed": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -53,6 +53,7 @@ class KMap:
     sparse: bool = False                      # sparse big level: centre product + offset-sorted stragglers (spconv_sparse.cu)
     rowptr: Optional[torch.Tensor] = None     # sparse: first contribution of every row
     contrib: Optional[torch.Tensor] = None    # sparse: scratch [stragglers, 32] fp32, rewritten by every conv on the level
+    tile_order: Optional[torch.Tensor] = None # um: the level's tiles, heaviest (most stream entries) first
 
 
 @dataclass
@@ -112,6 +113,7 @@ class GausPcgcCodec:
         self.adaptive_tiles = tile_rows is None       # tests: a fixed tile height / kernel variant of the mma.sync conv on every level
         self.tile_rows = int(tile_rows or 64)
         self.v6_variant = 42
+        self.um_order_tiles = True                    # tcgen05 conv: CTAs take the level's tiles heaviest first (shorter tail)
         self.um_tile_rows = 512                       # output rows per CTA of the tcgen05 conv (256 / 384 / 512 / 1024 are built)
         self._fns: Dict[str, object] = {}
         self._stream_h = None
@@ -340,7 +342,11 @@ class GausPcgcCodec:
         nbr = self._empty((max(n_pairs, 1),), torch.int32)
         off = self._empty((max(n_pairs, 1),), torch.int32)
         self._call("gpc_kmap_um_fill", _ptr(dense), n, tr, _ptr(seg), _ptr(nbr), _ptr(off), self._stream())
-        return KMap(seg, None, n_pairs, tr, n_real=n_real, um_rows=tr, pair_nbr=nbr, pair_off=off)
+        km = KMap(seg, None, n_pairs, tr, n_real=n_real, um_rows=tr, pair_nbr=nbr, pair_off=off)
+        if self.um_order_tiles:
+            starts = seg[::126].to(torch.int64)                  # first stream entry of every tile (+ the end of the last)
+            km.tile_order = torch.argsort(starts[1:] - starts[:-1], descending=True, stable=True).to(torch.int32)
+        return km
 
     def _sparse_map(self, dense: torch.Tensor, n: int) -> KMap:
         m = int(self.lib.gpc_kmap_sparse_segments(n))
@@ -442,7 +448,7 @@ class GausPcgcCodec:
             if rows is None:
                 self._prof_conv_begin()
             self._call("gpc_spconv_fwd_um", _ptr(xs), _ptr(self.w.convs_um[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(km.pair_off), n,
-                       km.um_rows, _ptr(residual), flags, _ptr(y), _ptr(ys), r0, r1, self._stream())
+                       km.um_rows, _ptr(km.tile_order), _ptr(residual), flags, _ptr(y), _ptr(ys), r0, r1, self._stream())
             if rows is None:
                 self._prof_conv_end(n, km)
             return y if fmt == "f32" else (ys if fmt == "split" else (y, ys))

@@ -105,6 +105,7 @@ template <int TM, int NMAX, int GS, int DS, int WS, int NPW, int NEW, int TCOLS,
 __global__ void __launch_bounds__((8 + NEW + (NPW > 3 ? NPW - 3 : 0)) * 32, MINB)
 spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_g, const unsigned char *__restrict__ xs, const uint4 *__restrict__ Wp,
                  const u32 *__restrict__ seg_g, const u32 *__restrict__ pair_nbr, const u32 *__restrict__ pair_off, i64 n, i64 tile0,
+                 const u32 *__restrict__ tile_order,
                  const void *__restrict__ residual, int flags, float *__restrict__ y, u32 *__restrict__ ys) {
     constexpr int NWARPS = 8 + NEW + (NPW > 3 ? NPW - 3 : 0), NTHREADS = NWARPS * 32;
     constexpr int RS = GS + DS;                  // row-offset ring: a chunk's entries live from its gather to the start of its epilogue
@@ -118,7 +119,9 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     Smem &s = *reinterpret_cast<Smem *>(smem_raw);
     if (((u32)__cvta_generic_to_shared(smem_raw) & 1023u) != 0u) __trap();      // 128 B swizzle atoms are 1024 B aligned
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const i64 t = tile0 + blockIdx.x;
+    // tile_order (full-level launches): heaviest tiles first, so that the last CTAs to start are the shortest (a level is only ~3
+    // tiles per CTA slot: in index order the SMs idle up to one tile's duration at the end of the launch)
+    const i64 t = tile0 + (tile_order ? (i64)tile_order[blockIdx.x] : (i64)blockIdx.x);
     long long pacc[4] = {0, 0, 0, 0}, t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t_begin = 0, t_setup = 0;
     UM_T(t_begin);
 
@@ -468,7 +471,7 @@ static um_encode_fn um_encoder() {
 
 template <int TM, int NMAX, int GS, int DS, int WS, int NPW, int NEW, int TCOLS, int MINB, bool PROF = false>
 static int launch_spconv_um(const CUtensorMap &tmap, const CUtensorMap &tmap_g, const void *xs, const void *Wp, const u32 *seg, const u32 *pair_nbr, const u32 *pair_off,
-                            i64 n, i64 tile0, i64 tiles, const void *residual, int flags, float *y, void *ys, cudaStream_t st) {
+                            i64 n, i64 tile0, i64 tiles, const u32 *tile_order, const void *residual, int flags, float *y, void *ys, cudaStream_t st) {
     static bool configured = false;
     typedef UmSmem<TM, NMAX, GS, DS, WS, NPW> Smem;
     constexpr size_t smem = sizeof(Smem);
@@ -479,7 +482,7 @@ static int launch_spconv_um(const CUtensorMap &tmap, const CUtensorMap &tmap_g, 
         configured = true;
     }
     spconv_um_kernel<TM, NMAX, GS, DS, WS, NPW, NEW, TCOLS, MINB, PROF><<<(unsigned)tiles, NTHREADS, smem, st>>>(
-        tmap, tmap_g, (const unsigned char *)xs, (const uint4 *)Wp, seg, pair_nbr, pair_off, n, tile0, residual, flags, y, (u32 *)ys);
+        tmap, tmap_g, (const unsigned char *)xs, (const uint4 *)Wp, seg, pair_nbr, pair_off, n, tile0, tile_order, residual, flags, y, (u32 *)ys);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
@@ -488,8 +491,8 @@ static int launch_spconv_um(const CUtensorMap &tmap, const CUtensorMap &tmap_g, 
 // tile_rows (512 or 1024) and pad = 16 (padding entries 0xFFFFFFFF), pair_off (gpc_kmap_um_count / _fill).  Output rows
 // [row0, row1) (whole tiles; row1 <= 0 or >= n: to the end).  y (fp32 rows) and / or ys (split rows).
 extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr,
-                                 const uint32_t *pair_off, int64_t n, int tile_rows, const void *residual, int flags, float *y,
-                                 void *ys, int64_t row0, int64_t row1, void *stream) {
+                                 const uint32_t *pair_off, int64_t n, int tile_rows, const uint32_t *tile_order, const void *residual,
+                                 int flags, float *y, void *ys, int64_t row0, int64_t row1, void *stream) {
     const bool prof = (flags & GPC_CONV_PROFILE) != 0;
     flags &= ~GPC_CONV_PROFILE;
     if (n <= 0) return GPC_OK;
@@ -518,20 +521,21 @@ extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t 
     if (rc2 != CUDA_SUCCESS) { gpc_set_error("cuTensorMapEncodeTiled (gather) failed: %d", (int)rc2); return GPC_ECUDA; }
     cudaStream_t st = as_stream(stream);
     const i64 tile0 = row0 / tile_rows, tiles = (row1 - row0 + tile_rows - 1) / tile_rows;
+    const u32 *order = (row0 == 0 && row1 == n) ? tile_order : nullptr;            // a permutation of the level's tiles: full launches only
     if (tile_rows == 256) {
-        if (prof) return launch_spconv_um<256, 64, 8, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
-        return launch_spconv_um<256, 64, 8, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
+        if (prof) return launch_spconv_um<256, 64, 8, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        return launch_spconv_um<256, 64, 8, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
     if (tile_rows == 384) {
-        if (prof) return launch_spconv_um<384, 64, 6, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
-        return launch_spconv_um<384, 64, 6, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
+        if (prof) return launch_spconv_um<384, 64, 6, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        return launch_spconv_um<384, 64, 6, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
     if (tile_rows == 512) {
-        if (prof) return launch_spconv_um<512, 64, 4, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
-        return launch_spconv_um<512, 64, 4, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
+        if (prof) return launch_spconv_um<512, 64, 4, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        return launch_spconv_um<512, 64, 4, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
-    if (prof) return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
-    return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, residual, flags, y, ys, st);
+    if (prof) return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+    return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
 }
 
 // W [n_kernels*125][32 ci][32 co] fp32 -> Wp [n_kernels*125][8 chunks][32 co][4 words]: channel co's TMEM lane is 32 words = 8 chunks of

@@ -206,9 +206,11 @@ int gpc_kmap_um_scan(const uint32_t *cell_counts, int64_t n, int tile_rows, uint
                      size_t ws_bytes, void *stream);
 int gpc_kmap_um_fill(const int32_t *map, int64_t n, int tile_rows, const uint32_t *seg, uint32_t *pair_nbr, uint32_t *pair_off,
                      void *stream);
+/* tile_order (optional, may be NULL): a permutation of the level's tile indices; CTA b of a FULL-level launch takes tile
+ * tile_order[b] (heaviest tiles first shortens the tail of the launch; results do not depend on it).  Ignored for row ranges. */
 int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t *seg, const uint32_t *pair_nbr, const uint32_t *pair_off,
-                      int64_t n, int tile_rows, const void *residual, int flags, float *y, void *ys, int64_t row0, int64_t row1,
-                      void *stream);
+                      int64_t n, int tile_rows, const uint32_t *tile_order, const void *residual, int flags, float *y, void *ys,
+                      int64_t row0, int64_t row1, void *stream);
 
 /* ---- a-6/a-9/a-12: embeddings ---- */
 /* Every producer of conv inputs writes fp32 rows (out), split rows (out_split: 32 x bf16 hi | 32 x bf16 lo, the operand format of

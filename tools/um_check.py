@@ -71,7 +71,8 @@ def main():
             poff = km.pair_off
             y = torch.full((n, 32), float("nan"), device=dev)
             ys = torch.zeros((n, 32), dtype=torch.int32, device=dev)
-            args = (_ptr(xs), _ptr(wp[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(poff), n, tr, _ptr(res), 1 | gflag, _ptr(y), _ptr(ys), 0, 0, st)
+            order = km.tile_order if os.environ.get("UM_ORDER", "1") != "0" else None
+            args = (_ptr(xs), _ptr(wp[widx]), _ptr(km.seg), _ptr(km.pair_nbr), _ptr(poff), n, tr, _ptr(order), _ptr(res), 1 | gflag, _ptr(y), _ptr(ys), 0, 0, st)
             rc = lib.gpc_spconv_fwd_um(*args)
             _lib.check(rc, "um")
             torch.cuda.synchronize()
@@ -82,11 +83,11 @@ def main():
             scale = float(ref_relu.abs().max())
             # determinism + row-range launches
             y2 = torch.empty_like(y)
-            args2 = list(args); args2[9] = _ptr(y2); args2[10] = None
+            args2 = list(args); args2[10] = _ptr(y2); args2[11] = None
             half = (n // 2) // tr * tr
-            a = list(args2); a[11], a[12] = 0, half
+            a = list(args2); a[12], a[13] = 0, half
             _lib.check(lib.gpc_spconv_fwd_um(*a), "um rows a")
-            a = list(args2); a[11], a[12] = half, 0
+            a = list(args2); a[12], a[13] = half, 0
             _lib.check(lib.gpc_spconv_fwd_um(*a), "um rows b")
             torch.cuda.synchronize()
             same = bool(torch.equal(y2, y))
@@ -98,7 +99,7 @@ def main():
             clk = ms * 1e-3 * 1.9e9 * 148 / max(n_pairs_real, 1)
             if os.environ.get("UM_PROF", "1") != "0":
                 lib.gpc_debug_conv_um_profile(None, 1)
-                a = list(args2); a[8] = 1 | 256 | gflag
+                a = list(args2); a[9] = 1 | 256 | gflag
                 _lib.check(lib.gpc_spconv_fwd_um(*a), "um prof")
                 buf = (C.c_uint64 * 16)()
                 lib.gpc_debug_conv_um_profile(C.cast(buf, C.c_void_p), 1)
