@@ -61,3 +61,49 @@ def gather_results(local, n_scenes: int, assignment: List[List[int]]):
             out[torch.tensor(idx, device=local.device)] = allr[r * longest: r * longest + len(idx)]
     assert len(assignment[rank]) == local.shape[0]
     return out
+
+
+# ----------------------------------------------------------------------------- inside one scene: Morton-ordered spatial blocks
+# The drop-in file (xyz_pcc.bin) codes a scene as ONE octree: every 5^3 context crosses the whole scene, so one scene is one
+# GPU's work.  For a scene that should be spread over several GPUs the rows -- already in
+# calculate_morton_order = ascending (z, y, x) order -- are cut into n_blocks consecutive ranges, i.e. z slabs, and every block
+# is coded as an independent point cloud with the unchanged codec: one file per block, each in the reference's own layout and
+# decodable by the reference's decompress_point_cloud.  Not the reference's single file: contexts stop at the block faces (a
+# few per cent more bits, measured in tools/block_split.py) and there are n_blocks headers; it is an opt-in beside the drop-in.
+def block_ranges(n_rows: int, n_blocks: int) -> List[tuple]:
+    """n_blocks consecutive row ranges of (almost) equal size covering [0, n_rows)"""
+    n_blocks = max(1, min(int(n_blocks), max(int(n_rows), 1)))
+    cuts = [(n_rows * b) // n_blocks for b in range(n_blocks + 1)]
+    return [(cuts[b], cuts[b + 1]) for b in range(n_blocks)]
+
+
+def block_path(output_path: str, b: int) -> str:
+    stem, ext = os.path.splitext(output_path)
+    return f"{stem}_blk{b}{ext}"
+
+
+def compress_point_cloud_blocks(xyz_sorted, ckpt_path: str, output_path: str, n_blocks: int, rank: int = 0, world_size: int = 1, **kw):
+    """Code the blocks b with b % world_size == rank of a scene given in calculate_morton_order order; block b goes to
+    block_path(output_path, b).  Returns {"blocks": [(b, rows, file_size_bits, enc_time)], "file_size_bits": this rank's sum}."""
+    from . import pcc_utils
+    out = []
+    for b, (r0, r1) in enumerate(block_ranges(xyz_sorted.shape[0], n_blocks)):
+        if b % world_size != rank:
+            continue
+        r = pcc_utils.compress_point_cloud(xyz_sorted[r0:r1], ckpt_path, block_path(output_path, b), **kw)
+        out.append((b, r1 - r0, int(r["file_size_bits"]), float(r["enc_time"])))
+    return {"blocks": out, "file_size_bits": sum(o[2] for o in out)}
+
+
+def decompress_point_cloud_blocks(output_path: str, ckpt_path: str, n_blocks: int, rank: int = 0, world_size: int = 1, **kw):
+    """Decode this rank's blocks; each block comes back in (z, y, x) order, so the blocks of all ranks concatenated by block index
+    are the scene in calculate_morton_order order.  Returns {"blocks": {b: point_cloud}, "dec_time": sum}."""
+    from . import pcc_utils
+    clouds, t = {}, 0.0
+    for b in range(n_blocks):
+        if b % world_size != rank:
+            continue
+        d = pcc_utils.decompress_point_cloud(block_path(output_path, b), ckpt_path, sorted_output=True, **kw)
+        clouds[b] = d["point_cloud"]
+        t += float(d["dec_time"])
+    return {"blocks": clouds, "dec_time": t}

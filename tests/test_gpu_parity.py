@@ -531,6 +531,31 @@ def test_edge_cases(env):
         codec.decode(np.zeros((1, 3), np.int32), np.array([1], np.uint8), [b"", b"", b""])
 
 
+def test_scene_as_morton_blocks(env, tmp_path):
+    """One scene cut into Morton-ordered spatial blocks (shard.compress_point_cloud_blocks), coded as if by two ranks: every block is
+    an ordinary xyz_pcc.bin, the blocks concatenated by index are the scene in calculate_morton_order order, few per cent more bits."""
+    from gauspcc_b200 import pcc_utils, shard
+    from gauspcc_b200.synth import hac_like_cloud
+    from gauspcc_b200.weights import save_synthetic_checkpoint
+    ckpt = save_synthetic_checkpoint(str(tmp_path / "GausPcgc" / "best_model_ue_4stage_conv.pt"))
+    x = torch.tensor(hac_like_cloud(60000, 8), dtype=torch.float32, device=env["dev"])
+    x = x[pcc_utils.calculate_morton_order(x)]
+    binp = str(tmp_path / "scene" / "xyz_pcc.bin")
+    whole = pcc_utils.compress_point_cloud(x, ckpt, binp)
+    enc = [shard.compress_point_cloud_blocks(x, ckpt, binp, 3, rank, 2) for rank in (0, 1)]
+    assert sorted(b for e in enc for b, *_ in e["blocks"]) == [0, 1, 2] and sum(r for e in enc for _, r, *_ in e["blocks"]) == 60000
+    dec = {}
+    for rank in (0, 1):
+        dec.update(shard.decompress_point_cloud_blocks(binp, ckpt, 3, rank, 2)["blocks"])
+    assert torch.equal(torch.cat([dec[b] for b in range(3)]), x)
+    bits = sum(e["file_size_bits"] for e in enc)
+    assert bits == 8 * sum(os.path.getsize(shard.block_path(binp, b)) for b in range(3))
+    assert whole["file_size_bits"] < bits < 1.05 * whole["file_size_bits"]
+    # a block file is an ordinary file of the drop-in format
+    d1 = pcc_utils.decompress_point_cloud(shard.block_path(binp, 1), ckpt)
+    assert d1["num_points"] == 20000
+
+
 def test_pcc_utils_api(env, tmp_path):
     """The drop-in boundary: same call pattern as HAC's conduct_encoding/conduct_decoding
     (scene/gaussian_model.py:1106-1121, 1248-1257)."""

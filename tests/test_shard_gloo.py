@@ -22,6 +22,23 @@ def test_assign_scenes_lpt():
     assert sorted(one[0]) == list(range(8))
 
 
+def test_block_ranges_and_pinning():
+    for n, k in [(10, 3), (1_000_000, 8), (5, 5), (2, 5), (0, 4), (7, 1)]:
+        r = shard.block_ranges(n, k)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert len(r) == max(1, min(k, max(n, 1))) and max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
+    assert shard.block_path("/a/b/xyz_pcc.bin", 3) == "/a/b/xyz_pcc_blk3.bin"
+    before = os.sched_getaffinity(0)
+    try:
+        got = shard.pin_rank(0, 1)
+        assert got == len(before) and os.sched_getaffinity(0) == before          # one rank keeps every CPU
+        if len(before) >= 4:
+            assert shard.pin_rank(1, 2) == len(before) // 2
+            assert os.sched_getaffinity(0) == set(sorted(before)[len(before) // 2:2 * (len(before) // 2)])
+    finally:
+        os.sched_setaffinity(0, before)
+
+
 def _worker(rank, world, port, sizes, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
