@@ -29,6 +29,10 @@
 #include <cuda.h>
 #include "umma.cuh"
 
+#ifndef UM_MIX_DEN
+#define UM_MIX_DEN 2         // UM_GATHER_TMA == 2: chunks with c % UM_MIX_DEN < UM_MIX_TMA go through TMA, the others through cp.async
+#define UM_MIX_TMA 1
+#endif
 #ifndef UM_GATHER_TMA
 #define UM_GATHER_TMA 1      // 1: the rows of the non-centre offsets by TMA tile::gather4 (A/B, profiles/r02_conv_um.md); 0: cp.async
 #endif
@@ -195,7 +199,7 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             UM_T(t2);
             if (c >= (u32)DS) UM_WAIT(empty_d0 + ds * 8, ((c / (u32)DS) & 1u) ^ 1u);
             UM_T(t3);
-            if (!UM_GATHER_TMA) fence_async_smem();              // rows written by cp.async (generic proxy) -> visible to the tensor core
+            if (UM_GATHER_TMA != 1) fence_async_smem();          // rows written by cp.async (generic proxy) -> visible to the tensor core
             tmem_fence_after();
             if (elect_one()) {
                 const u32 idesc = IDESC | ((len >> 3) << 17);
@@ -256,7 +260,7 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                                  ::"r"(slot), "l"(reinterpret_cast<u64>(&tmap)), "r"(bar), "r"(0), "r"((int)(t * TM + j * NMAX)) : "memory");
                 }
-            } else if (UM_GATHER_TMA) {
+            } else if (UM_GATHER_TMA == 1 || (UM_GATHER_TMA == 2 && (c % UM_MIX_DEN) < UM_MIX_TMA)) {
                 // TMA tile::gather4: four arbitrary rows per instruction, written with the 128 B swizzle; padding entries (row -1) are
                 // out of bounds = zero fill.  Issued by ONE elected lane inside warp-uniform control flow (per-lane issue makes ptxas
                 // emit an election loop with six R2UR.BROADCAST per instruction: ~50-100 clk each, profiles/r02_conv_um.md).
