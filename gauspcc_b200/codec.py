@@ -38,6 +38,9 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+COORD_LIMIT = (1 << 20) - 16           # |voxel coordinate| the 21-bit key fields hold with room for the 5^3 neighbourhood
+
+
 @dataclass
 class KMap:
     """Kernel map of one coordinate set (built once, shared by every conv on the set), in the form its conv kernel consumes."""
@@ -307,6 +310,17 @@ class GausPcgcCodec:
         if n >= 1_500:
             return 16, 46
         return 8, 47
+
+    def _recentre(self, xyz: torch.Tensor):
+        """xyz - shift with shift a per-axis multiple of 2^(bits of the extent + 1) (>= 2^levels: floor(c / 2^l) commutes with it on
+        every level) that centres the scene on the origin; ValueError if the extent itself exceeds the key fields."""
+        lo = xyz.amin(0).to(torch.int64).cpu().numpy()
+        hi = xyz.amax(0).to(torch.int64).cpu().numpy()
+        G = 1 << (int((hi - lo).max()).bit_length() + 1)
+        shift = ((lo + hi) // 2 + G // 2) // G * G
+        if max(int(np.abs(hi - shift).max()), int(np.abs(lo - shift).max())) > COORD_LIMIT:
+            raise ValueError(f"voxel coordinates must lie within +-{COORD_LIMIT}, or span less than ~{COORD_LIMIT * 2 // 5} voxels anywhere")
+        return xyz - torch.tensor(shift, dtype=xyz.dtype, device=xyz.device), shift
 
     def _count_pairs(self, dense: torch.Tensor, n: int, tr: int, pad: int):
         """first pass over the dense map: seg (exclusive scan of the padded per-(tile, offset) counts), entries, true pairs"""
@@ -647,8 +661,15 @@ class GausPcgcCodec:
         meta_h = meta.cpu().numpy()
         if meta_h[0] & 1:
             raise ValueError("compress_point_cloud expects voxelised (integral) coordinates")
+        shift = None
         if meta_h[0] & 2:
-            raise ValueError(f"voxel coordinates must lie within +-{(1 << 20) - 16}")
+            # outside the 21-bit key fields: code the scene translated towards the origin (the pyramid is translation-invariant for
+            # offsets that are multiples of 2^levels; the base level is written in the caller's coordinates again at the end)
+            xyz, shift = self._recentre(xyz)
+            with self._stage("order", 0):
+                keys, meta = self.pack_keys(xyz)
+            meta_h = meta.cpu().numpy()
+            assert not (meta_h[0] & 2)
         mm = meta_h[2:8].astype(np.uint32)
         with self._stage("order", 0):
             leaf = self.sort_unique(keys, mm)
@@ -709,6 +730,13 @@ class GausPcgcCodec:
         base_xyz = self._empty((base.n, 3), torch.int32)
         self._call("gpc_unpack_keys_i32", _ptr(base.keys), base.n, _ptr(base_xyz), self._stream())
         base_xyz_h = base_xyz.cpu().numpy()
+        if shift is not None:
+            depth = L + 1                              # the base level is the leaves' ancestors depth levels up
+            assert not np.any(shift % (1 << depth)), "translation must be a multiple of 2^depth"
+            moved = base_xyz_h.astype(np.int64) + (shift >> depth)
+            if np.abs(moved).max(initial=0) >= (1 << 31):
+                raise ValueError("base coordinates do not fit int32")
+            base_xyz_h = moved.astype(np.int32)
         base_occ_h = base.occ.cpu().numpy()
         self._seg_end()
         gpu_ms = self._seg_total_ms()                  # synchronises: all D2H copies have landed
@@ -977,7 +1005,20 @@ class GausPcgcCodec:
         if len(streams) % 4:
             raise ValueError("stream count must be a multiple of 4 (one group per octree level)")
         self._seg_begin()
-        bx = torch.from_numpy(np.array(base_xyz, dtype=np.int32).reshape(-1, 3)).to(self.dev)
+        bx_h = np.array(base_xyz, dtype=np.int32).reshape(-1, 3)
+        L = len(streams) // 4 + 1                      # leaves are 2^L base voxels wide: one level per stream group + the base's own occupancy
+        shift = None
+        if bx_h.size and (int(np.abs(bx_h.astype(np.int64)).max()) + 1) << L > COORD_LIMIT:
+            # some leaf of the base voxels may lie outside the 21-bit key fields: decode translated (children are 2c + b, so any base
+            # translation t is a leaf translation t * 2^L) and add it back on the decoded rows.  If even the centred scene does not
+            # fit, the encoder cannot have translated either (it would have refused): the file is of a scene near the origin that
+            # spans nearly the whole range, and decodes as it is.
+            b64 = bx_h.astype(np.int64)
+            t = (b64.min(axis=0) + b64.max(axis=0) + 1) // 2
+            if max(int(-(b64.min(axis=0) - t).min()) << L, ((int((b64.max(axis=0) - t).max()) + 1) << L) - 1) <= COORD_LIMIT:
+                bx_h = (b64 - t).astype(np.int32)
+                shift = t << L
+        bx = torch.from_numpy(bx_h).to(self.dev)
         bo = torch.from_numpy(np.array(base_occ, dtype=np.uint8).reshape(-1)).to(self.dev)
         keys, meta = self.pack_keys(bx)
         meta_h = meta.cpu().numpy()
@@ -1038,14 +1079,19 @@ class GausPcgcCodec:
             cur = child
         n_pts = self._popcount(cur.occ)
         out = self._empty((n_pts, 3), torch.float32)
+        k_scale = float(scale) if shift is None else 1.0
         if sorted_rows:
             ck, _ = self.expand(cur, n_pts)            # child keys already in (z,y,x) order: closed-form ranks, no sort
-            self._call("gpc_unpack_keys_f32", _ptr(ck), n_pts, float(scale), _ptr(out), self._stream())
+            self._call("gpc_unpack_keys_f32", _ptr(ck), n_pts, k_scale, _ptr(out), self._stream())
         else:
             ws_b = self.lib.gpc_expand_workspace_bytes(cur.n)
             ws = self._ws(ws_b)
-            self._call("gpc_expand_leaves_f32", _ptr(cur.keys), _ptr(cur.occ), cur.n, n_pts, float(scale), _ptr(out), _ptr(ws), ws_b,
+            self._call("gpc_expand_leaves_f32", _ptr(cur.keys), _ptr(cur.occ), cur.n, n_pts, k_scale, _ptr(out), _ptr(ws), ws_b,
                        self._stream())
+        if shift is not None:                          # integers below 2^24 add exactly in fp32, as in the reference's own float rows
+            out += torch.tensor(shift, dtype=torch.float32, device=self.dev)
+            if float(scale) != 1.0:
+                out *= float(scale)
         self._seg_end()
         self._stream_h = None
         # host_ac_s: seconds inside the range decoder on the critical path (wavefront levels: the slowest of the four concurrent

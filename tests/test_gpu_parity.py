@@ -525,10 +525,34 @@ def test_edge_cases(env):
         assert np.array_equal(np.unique(dec, axis=0), np.unique(xyz, axis=0))
     with pytest.raises(ValueError):
         codec.encode(torch.tensor([[0.25, 0, 0]], dtype=torch.float32, device=dev))
-    with pytest.raises(ValueError):
-        codec.encode(torch.tensor([[1 << 20, 0, 0]], dtype=torch.int32, device=dev))
+    with pytest.raises(ValueError):                                                    # extent beyond the key fields
+        codec.encode(torch.tensor([[0, 0, 0], [1 << 21, 0, 0]], dtype=torch.int32, device=dev))
     with pytest.raises(ValueError):
         codec.decode(np.zeros((1, 3), np.int32), np.array([1], np.uint8), [b"", b"", b""])
+
+
+def test_far_from_origin_vs_oracle(env, weights_np):
+    """Coordinates outside the 21-bit key fields (|c| > 2^20 - 16): the scene is coded translated by a multiple of 2^levels and the
+    base level written back in the caller's coordinates, so file and decoded rows are those of the oracle (reference arithmetic on
+    int32 coordinates, no range limit) -- for float and int input, default and sorted row order, and a single far voxel."""
+    from gauspcc_b200 import bitstream
+    from gauspcc_b200.synth import hac_like_cloud
+    from oracle import oracle as O
+    codec = env["codec"]
+    off = np.array([3_000_000, -5_000_000, 7_000_123], dtype=np.int32)
+    for xyz in (hac_like_cloud(6000, 2, extent_log2=13) + off, np.array([[1 << 20, 0, -(1 << 22)]], dtype=np.int32)):
+        ref = O.encode(xyz, weights_np)
+        for dt in (torch.int32, torch.float32):
+            blob, (bx, bo, streams), _ = _encode_file(codec, torch.tensor(xyz, dtype=dt, device=codec.dev))
+            _, rbx, rbo, rst = bitstream.read_file(ref)
+            assert np.array_equal(bx, rbx) and np.array_equal(bo, rbo) and len(streams) == len(rst)
+            assert abs(len(blob) - len(ref)) <= max(4, SIZE_TOL * len(ref))
+            dec = codec.decode(bx, bo, streams).cpu().numpy()
+            assert np.array_equal(dec, O.decode(ref, weights_np))
+            srt = codec.decode(bx, bo, streams, sorted_rows=True).cpu().numpy().astype(np.int64)
+            assert np.array_equal(srt, xyz[np.lexsort((xyz[:, 0], xyz[:, 1], xyz[:, 2]))])
+        scaled = codec.decode(bx, bo, streams, scale=0.5).cpu().numpy()
+        assert np.array_equal(scaled, dec * np.float32(0.5))
 
 
 def test_scene_as_morton_blocks(env, tmp_path):
