@@ -135,6 +135,7 @@ class GausPcgcCodec:
         self.wave_streams = True
         self._wave_side: Optional[list] = None
         self._wave_buf: Optional[torch.Tensor] = None
+        self._coder_arena = None                      # (c_low, c_high) words of all streams of a scene (container version 2)
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
         self.debug_dec_cdfs: Optional[dict] = None    # tests: (level, stage) -> CDF rows the stage-by-stage decoder computed
         self.wave_first_rows = 8192                   # size / number of the small leading chunks
@@ -616,6 +617,83 @@ class GausPcgcCodec:
                 self._call("gpc_head_cdf", _ptr(t), n, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), W.STAGE_ALPHABETS[i], _ptr(cdf_out),
                            _ptr(prob_out), self._stream())
 
+    # ------------------------------------------------------------------ GPU chunk coder (container version 2)
+    def _chunk_begin(self, stream_rows: List[int], chunk: int):
+        """Version-2 encode: ONE device array holds the (c_low, c_high) words of every stream of the scene, each stream padded to
+        whole chunks with zero words -- a zero word is the symbol [0, 0x10000): it leaves the coder's interval unchanged and costs
+        no bits, so a stream's last chunk is the stream of its real symbols.  The head kernels write their words straight into it;
+        at the end ONE launch codes all chunks of all streams at once (a chunk is one warp walking a serial chain: ten thousand of
+        them side by side take as long as one)."""
+        starts, total = [], 0
+        for n in stream_rows:
+            starts.append(total)
+            total += (n + chunk - 1) // chunk * chunk
+        if self._coder_arena is None or self._coder_arena.numel() < total:
+            self._coder_arena = torch.empty(int(total * 1.25) + chunk, dtype=torch.int32, device=self.dev)
+        self._coder_arena[:total].zero_()
+        self._coder_starts, self._coder_total, self._coder_rows = starts, total, list(stream_rows)
+
+    def _chunk_slot(self, k: int) -> torch.Tensor:
+        return self._coder_arena[self._coder_starts[k]:self._coder_starts[k] + self._coder_rows[k]]
+
+    def _chunk_finish(self, chunk: int) -> List[bytes]:
+        """code every chunk of every stream in one launch, bring counts and bytes to the host in one staging copy each"""
+        total = self._coder_total
+        if total == 0:
+            return []
+        chunks = total // chunk
+        cnt = self._empty((chunks,), torch.int32)
+        offs = self._empty((chunks + 1,), torch.int32)
+        ws_b = self.lib.gpc_attr_workspace_bytes(total, chunk)
+        ws = self._ws(ws_b)
+        self._call("gpc_chunk_encode_lohi", _ptr(self._coder_arena), total, chunk, _ptr(cnt), _ptr(offs), _ptr(ws), ws_b, self._stream())
+        cnt_h = cnt.cpu().numpy()                                               # synchronises; offsets on the host from the counts
+        if cnt_h.size and int(cnt_h.max()) > 0xFFFF:
+            raise ValueError("chunk too long for the u16 byte counts of container version 2")
+        offs_h = np.concatenate([[0], np.cumsum(cnt_h, dtype=np.int64)])
+        nbytes = int(offs_h[-1])
+        out = self._empty((nbytes + 64,), torch.uint8)
+        self._call("gpc_attr_merge_chunks", _ptr(ws), total, chunk, _ptr(offs), _ptr(out), self._stream())
+        pin = self._pin(nbytes + 64)
+        pin[:nbytes].copy_(out[:nbytes], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        host = pin.numpy()
+        streams = []
+        for start, n in zip(self._coder_starts, self._coder_rows):
+            c0, c1 = start // chunk, start // chunk + (n + chunk - 1) // chunk
+            streams.append(cnt_h[c0:c1].astype("<u2").tobytes() + host[int(offs_h[c0]):int(offs_h[c1])].tobytes())
+        return streams
+
+    def _chunk_upload(self, streams: List[bytes]):
+        """all version-2 streams of a file -> device in ONE staging copy (a 1M-anchor scene is ~9 MB); per stream its offset"""
+        offs, total = [], 0
+        for sb in streams:
+            offs.append(total)
+            total += (len(sb) + 255) // 256 * 256
+        pin = self._pin(total + 256)
+        host = pin.numpy()
+        for o, sb in zip(offs, streams):
+            host[o:o + len(sb)] = np.frombuffer(sb, dtype=np.uint8)
+        dev = torch.empty(total + 256, dtype=torch.uint8, device=self.dev)
+        dev[:total].copy_(pin[:total], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()        # the staging buffer is free again (the GPU is idle here anyway)
+        return dev, offs
+
+    def _chunk_decode(self, cdf_d: torch.Tensor, stream: bytes, dev_bytes: torch.Tensor, off: int, n: int, Lp: int, chunk: int) -> torch.Tensor:
+        chunks = (n + chunk - 1) // chunk
+        if len(stream) < 2 * chunks:
+            raise ValueError("truncated version-2 stream")
+        cnt_h = np.frombuffer(stream, dtype="<u2", count=chunks)
+        if int(cnt_h.astype(np.int64).sum()) != len(stream) - 2 * chunks:
+            raise ValueError("corrupt version-2 stream (chunk byte counts)")
+        cnt = dev_bytes[off:off + 2 * chunks].view(torch.int16).to(torch.int32) & 0xFFFF          # u16 counts, widened on the device
+        sym = self._empty((n,), torch.uint8)
+        ws_b = self.lib.gpc_attr_workspace_bytes(n, chunk)
+        ws = self._ws(ws_b)
+        self._call("gpc_chunk_decode_u16", _ptr(cdf_d), C.c_void_p(dev_bytes.data_ptr() + off + 2 * chunks), _ptr(cnt), n, Lp, chunk,
+                   _ptr(sym), _ptr(ws), ws_b, self._stream())
+        return sym
+
     # ------------------------------------------------------------------ host range coder
     def _ac_encode(self, cdf: np.ndarray, sym: np.ndarray) -> bytes:
         n, Lp = cdf.shape
@@ -644,11 +722,14 @@ class GausPcgcCodec:
                                             sym_out.ctypes.data_as(C.c_void_p)), "gpc_ac_decode_h")
 
     # ------------------------------------------------------------------ encode
-    def encode(self, xyz: torch.Tensor, collect: bool = False, download: bool = True):
+    def encode(self, xyz: torch.Tensor, collect: bool = False, download: bool = True, gpu_chunk: int = 0):
         """[N,3] CUDA float32/int32 voxel indices -> (base_xyz int32 [n0,3], base_occ u8 [n0], streams, aux).
 
         download=False (bench, device-timed number): the CDF rows and symbols stay in HBM, nothing is copied to
         the host and the range coder does not run (streams is None); the device work is unchanged.
+        gpu_chunk > 0 (container version 2; NOT the reference bitstream): the streams are coded on the GPU in chunks
+        of gpu_chunk symbols (csrc/attr_ac.cu: one warp per chunk) -- no host range coder, only compressed bytes cross PCIe.
+        A stream is then `u16 bytes_of_chunk[chunks]` followed by the chunks' bytes.
         """
         self._launch_base = int(self.lib.gpc_launch_count())
         self._segments = []
@@ -699,6 +780,8 @@ class GausPcgcCodec:
                     with self._stage("kmap", self._kmap_bytes(lv.n)):
                         lv.kmap = self.build_kmap(lv.keys)
         level_futs = [[] for _ in range(L)]
+        if download and gpu_chunk:
+            self._chunk_begin([levels[k // 4 + 1].n for k in range(4 * L)], gpu_chunk)
         if collect:
             aux["child_keys"], aux["probs"], aux["cdfs"] = [None] * L, [None] * (4 * L), [None] * (4 * L)
         for d in range(L - 1, -1, -1):
@@ -711,16 +794,18 @@ class GausPcgcCodec:
                 A = W.STAGE_ALPHABETS[i]
                 cdf_d = self._empty((gt.n, A + 1), torch.int16) if collect else None
                 prob_d = self._empty((gt.n, A), torch.float32) if collect else None
-                lohi_d = self._empty((gt.n,), torch.int32)
+                lohi_d = self._chunk_slot(4 * d + i) if (download and gpu_chunk) else self._empty((gt.n,), torch.int32)
                 self.stage_cdf(u, gt.occ, i, child.kmap, cdf_d, prob_d, lohi_out=lohi_d)
-                if download:
+                if download and gpu_chunk:
+                    pass                                                        # coded with all other streams at the end (_chunk_finish)
+                elif download:
                     lohi_h = carve(gt.n * 4, torch.int32, (gt.n,))
                     lohi_h.copy_(lohi_d, non_blocking=True)
                     level_jobs.append(lohi_h)
                 if collect:
                     aux["probs"][4 * d + i] = prob_d
                     aux["cdfs"][4 * d + i] = cdf_d
-            if download:
+            if download and not gpu_chunk:
                 ready = torch.cuda.Event(blocking=True)          # the coder threads sleep on it instead of spinning
                 ready.record(torch.cuda.current_stream(self.dev))
                 # host range coding of this level overlaps the GPU work of the coarser levels
@@ -741,6 +826,8 @@ class GausPcgcCodec:
         self._seg_end()
         gpu_ms = self._seg_total_ms()                  # synchronises: all D2H copies have landed
         streams = [f.result() for f in futs] if download else None
+        if download and gpu_chunk:
+            streams = self._chunk_finish(gpu_chunk)
         self._stream_h = None
         self.last_stats = {"gpu_ms": gpu_ms, "launches": self.launches, "rows": rows, "levels": L,
                            "d2h_bytes": cursor, "n_unique": int(leaf.shape[0])}
@@ -991,7 +1078,7 @@ class GausPcgcCodec:
         return t_wait, max(ac_s)
 
     def decode(self, base_xyz: np.ndarray, base_occ: np.ndarray, streams: List[bytes], scale: float = 1.0,
-               forced_occ: Optional[List[torch.Tensor]] = None, sorted_rows: bool = False) -> torch.Tensor:
+               forced_occ: Optional[List[torch.Tensor]] = None, sorted_rows: bool = False, gpu_chunk: int = 0) -> torch.Tensor:
         """-> float32 [N,3] CUDA, rows in the reference's order (children of (z,y,x)-sorted parents, octant ascending), or,
         with sorted_rows, in ascending (z,y,x) == calculate_morton_order order (the caller's re-sort,
         HAC/scene/gaussian_model.py:1253-1255, becomes the identity).
@@ -1034,6 +1121,8 @@ class GausPcgcCodec:
         self._call("gpc_sort_pairs", _ptr(keys), _ptr(None), _ptr(skeys), _ptr(perm), n0, xf, _ptr(ws), ws_b, self._stream())
         cur = Level(skeys, bo[perm.long()] if n0 else bo, n0)
         pin = self._pinned_dec                     # staging for CDF rows / symbols, kept across calls (grown geometrically)
+        if gpu_chunk and forced_occ is None:
+            v2_dev, v2_off = self._chunk_upload(streams)
         t_wait = t_ac = 0.0
         n_wave = 0
         for g in range(0, len(streams), 4):
@@ -1042,6 +1131,18 @@ class GausPcgcCodec:
             occ = torch.zeros(n_child, dtype=torch.uint8, device=self.dev)
             if forced_occ is None and (pin is None or pin.numel() < n_child * 40):
                 pin = self._pinned_dec = torch.empty(int(n_child * 40 * 1.5) + 4096, dtype=torch.uint8, pin_memory=True)
+            if forced_occ is None and gpu_chunk:
+                # container version 2: the stage's symbols are decoded on the GPU from the CDF rows where they lie; nothing crosses
+                # PCIe but the compressed bytes, no host coder, no wavefront needed
+                for i in range(4):
+                    A = W.STAGE_ALPHABETS[i]
+                    cdf_d = self._empty((n_child, A + 1), torch.int16)
+                    self.stage_cdf(u, occ, i, child.kmap, cdf_d)
+                    sym_d = self._chunk_decode(cdf_d, streams[g + i], v2_dev, v2_off[g + i], n_child, A + 1, gpu_chunk)
+                    self._call("gpc_merge_symbol", _ptr(occ), n_child, STAGE_SHIFT[i], _ptr(sym_d), self._stream())
+                child.occ = occ
+                cur = child
+                continue
             if forced_occ is None and self._wave_ok(child, n_child):
                 dw, da = self._decode_level_wavefront(u, child, n_child, streams[g:g + 4], occ)
                 t_wait += dw

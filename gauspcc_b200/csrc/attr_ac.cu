@@ -52,6 +52,14 @@ struct TableModel {
     __device__ __forceinline__ Row row(i64 r) const { return Row{r * Lp}; }
     __device__ __forceinline__ u32 v(const Row &rw, int m) const { return (u32)(__float2int_rn(cdf[rw.base + m] * scale16) + m); }
 };
+// integer CDF rows as the geometry codec's head kernel writes them (uint16 bit pattern of kit/op.py:67-79; the top of the last
+// symbol is 0x10000 by rule): the chunked coder on the occupancy symbols themselves (container version 2)
+struct U16Model {
+    const u16 *cdf; int Lp;
+    struct Row { i64 base; };
+    __device__ __forceinline__ Row row(i64 r) const { return Row{r * Lp}; }
+    __device__ __forceinline__ u32 v(const Row &rw, int m) const { return (u32)cdf[rw.base + m]; }
+};
 struct GaussModel {
     const float *mean, *scale, *Q; int min_value; float scale16;
     struct Row { float mean, scale, q; };
@@ -108,8 +116,20 @@ struct BitWriter {
     }
 };
 
+struct BoundsLoad {                                  // (c_low, c_high) as attr_bounds_kernel wrote them
+    const uint2 *p;
+    __device__ __forceinline__ uint2 operator()(i64 i) const { return p[i]; }
+};
+struct LohiLoad {                                    // c_low | c_high << 16, c_high == 0 meaning 0x10000 (gpc_head_cdf_sym)
+    const u32 *p;
+    __device__ __forceinline__ uint2 operator()(i64 i) const {
+        const u32 e = p[i];
+        return make_uint2(e & 0xFFFFu, (e >> 16) ? (e >> 16) : 0x10000u);
+    }
+};
 // one warp per chunk (:94-163).  Every lane runs the coder on the same values; lane 0 writes.
-__global__ void __launch_bounds__(128) attr_encode_chunks_kernel(const uint2 *__restrict__ bounds, i64 n, int chunk_size, int chunks,
+template <typename Load>
+__global__ void __launch_bounds__(128) attr_encode_chunks_kernel(Load bounds, i64 n, int chunk_size, int chunks,
                                                                 u8 *__restrict__ cache, i64 cap, i32 *__restrict__ cnt,
                                                                 int *__restrict__ status) {
     const int lane = threadIdx.x & 31;
@@ -121,10 +141,10 @@ __global__ void __launch_bounds__(128) attr_encode_chunks_kernel(const uint2 *__
     const bool store = lane == 0;
     u32 low = 0u, high = 0xFFFFFFFFu;
     u64 pending = 0;
-    uint2 nxt = lane < len ? bounds[base + lane] : make_uint2(0u, 0u);
+    uint2 nxt = lane < len ? bounds(base + lane) : make_uint2(0u, 0u);
     for (int j0 = 0; j0 < len; j0 += 32) {
         const uint2 cur = nxt;
-        if (j0 + 32 + lane < len) nxt = bounds[base + j0 + 32 + lane];
+        if (j0 + 32 + lane < len) nxt = bounds(base + j0 + 32 + lane);
         const int m = min(32, len - j0);
         for (int j = 0; j < m; ++j) {
             const u64 c_low = __shfl_sync(0xFFFFFFFFu, cur.x, j);
@@ -219,10 +239,10 @@ __device__ __forceinline__ int attr_search(const Model &md, const typename Model
     return lo;
 }
 
-template <typename Model, bool CENTRED>
+template <typename Model, bool CENTRED, typename SymT>
 __global__ void __launch_bounds__(128) attr_decode_chunks_kernel(Model md, const u8 *__restrict__ in, const u32 *__restrict__ offsets,
                                                                 i64 n, int chunk_size, int chunks, int max_symbol,
-                                                                int16_t *__restrict__ out) {
+                                                                SymT *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= chunks) return;
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(128) attr_decode_chunks_kernel(Model md, const
                 }
             }
         }
-        if (lane < m) out[base + j0 + lane] = (int16_t)my_sym;
+        if (lane < m) out[base + j0 + lane] = (SymT)my_sym;
     }
 }
 
@@ -347,7 +367,7 @@ int attr_encode(Model md, const int16_t *sym, i64 n, int Lp, int chunk_size, i32
     if (n == 0) { GPC_CUDA_CHECK(cudaMemsetAsync(offsets, 0, 4, st)); return GPC_OK; }
     attr_bounds_kernel<Model><<<cdiv(n, 256), 256, 0, st>>>(md, sym, n, Lp - 2, L.bounds, L.status);
     GPC_LAUNCH_CHECK();
-    attr_encode_chunks_kernel<<<cdiv(chunks, 4), 128, 0, st>>>(L.bounds, n, chunk_size, chunks, L.cache, L.cap, cnt, L.status);
+    attr_encode_chunks_kernel<BoundsLoad><<<cdiv(chunks, 4), 128, 0, st>>>(BoundsLoad{L.bounds}, n, chunk_size, chunks, L.cache, L.cap, cnt, L.status);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{(const u32 *)cnt};
     int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);
@@ -355,8 +375,8 @@ int attr_encode(Model md, const int16_t *sym, i64 n, int Lp, int chunk_size, i32
     return attr_status(L, st, "attribute encoder");
 }
 
-template <typename Model, bool CENTRED>
-int attr_decode(Model md, const u8 *in, const i32 *cnt, i64 n, int Lp, int chunk_size, int16_t *sym, void *ws, size_t ws_bytes,
+template <typename Model, bool CENTRED, typename SymT>
+int attr_decode(Model md, const u8 *in, const i32 *cnt, i64 n, int Lp, int chunk_size, SymT *sym, void *ws, size_t ws_bytes,
                 cudaStream_t st) {
     AttrWs L;
     GPC_REQUIRE(ws && ws_bytes >= attr_layout(n, chunk_size, ws, &L), GPC_ENOSPC, "workspace too small");
@@ -366,7 +386,7 @@ int attr_decode(Model md, const u8 *in, const i32 *cnt, i64 n, int Lp, int chunk
     PtrLoad<u32> pl{(const u32 *)cnt};
     int rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);   // compute_cumsum, :358-363
     if (rc) return rc;
-    attr_decode_chunks_kernel<Model, CENTRED><<<cdiv(chunks, 4), 128, 0, st>>>(md, in, offsets, n, chunk_size, chunks, Lp - 2, sym);
+    attr_decode_chunks_kernel<Model, CENTRED, SymT><<<cdiv(chunks, 4), 128, 0, st>>>(md, in, offsets, n, chunk_size, chunks, Lp - 2, sym);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
@@ -422,7 +442,7 @@ extern "C" int gpc_attr_decode_table(const float *cdf, const uint8_t *in, const 
     int rc = attr_check(n, Lp, chunk_size);
     if (rc) return rc;
     TableModel md{cdf, Lp, (float)((1 << ATTR_PRECISION) - (Lp - 1))};
-    return attr_decode<TableModel, false>(md, in, cnt, n, Lp, chunk_size, sym, ws, ws_bytes, as_stream(stream));
+    return attr_decode<TableModel, false, int16_t>(md, in, cnt, n, Lp, chunk_size, sym, ws, ws_bytes, as_stream(stream));
 }
 
 extern "C" int gpc_attr_decode_gaussian(const float *mean, const float *scale, const float *Q, const uint8_t *in, const int32_t *cnt,
@@ -432,5 +452,106 @@ extern "C" int gpc_attr_decode_gaussian(const float *mean, const float *scale, c
     int rc = attr_check(n, Lp, chunk_size);
     if (rc) return rc;
     GaussModel md{mean, scale, Q, min_value, (float)((1 << ATTR_PRECISION) - (Lp - 1))};
-    return attr_decode<GaussModel, true>(md, in, cnt, n, Lp, chunk_size, sym, ws, ws_bytes, as_stream(stream));
+    return attr_decode<GaussModel, true, int16_t>(md, in, cnt, n, Lp, chunk_size, sym, ws, ws_bytes, as_stream(stream));
+}
+
+// ---- the same chunked coder on the geometry codec's own symbols (container version 2): the occupancy streams of a
+// level coded on the GPU in chunks instead of by one serial host coder per stream.  Not the reference's bitstream (torchac codes a
+// stream as ONE coder): an opt-in container next to the drop-in one.
+extern "C" int gpc_chunk_encode_lohi(const uint32_t *lohi, int64_t n, int chunk_size, int32_t *cnt, uint32_t *offsets, void *ws,
+                                     size_t ws_bytes, void *stream) {
+    int rc = attr_check(n, 3, chunk_size);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    AttrWs L;
+    GPC_REQUIRE(ws && ws_bytes >= attr_layout(n, chunk_size, ws, &L), GPC_ENOSPC, "workspace too small");
+    const int chunks = (int)((n + chunk_size - 1) / chunk_size);
+    GPC_CUDA_CHECK(cudaMemsetAsync(L.status, 0, 4, st));
+    if (n == 0) { GPC_CUDA_CHECK(cudaMemsetAsync(offsets, 0, 4, st)); return GPC_OK; }
+    attr_encode_chunks_kernel<LohiLoad><<<cdiv(chunks, 4), 128, 0, st>>>(LohiLoad{lohi}, n, chunk_size, chunks, L.cache, L.cap, cnt, L.status);
+    GPC_LAUNCH_CHECK();
+    PtrLoad<u32> pl{(const u32 *)cnt};
+    return device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);     // no host synchronisation
+}
+
+// Decoder of the geometry streams: alphabets of 2 / 2 / 4 / 16 symbols, so a whole CDF row (Lp <= 32 entries) is ONE coalesced load,
+// lane m holding entry m, and the symbol is a ballot.  The rows do not depend on the decoded symbols: the row of symbol i + 1 is
+// requested before symbol i is decoded, which takes the load latency off the serial chain.
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(128) chunk_decode_u16_kernel(const u16 *__restrict__ cdf, int Lp, const u8 *__restrict__ in,
+                                                              const u32 *__restrict__ offsets, i64 n, int chunk_size, int chunks,
+                                                              u8 *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= chunks) return;
+    const i64 base = (i64)w * chunk_size;
+    const int len = (int)min((i64)chunk_size, n - base);
+    const int max_symbol = Lp - 2;
+    BitReader br;
+    br.init(in + offsets[w], (i64)(offsets[w + 1] - offsets[w]), lane);
+    u32 low = 0u, high = 0xFFFFFFFFu;
+    u32 value = br.get(32, lane);
+    const u16 *row = cdf + base * Lp;
+    // lane m: entry m of the row; entries above the top symbol read as 0x10000 (the top of the last symbol, by rule)
+    auto load_row = [&](int i) -> u32 { return lane <= max_symbol ? (u32)row[(i64)i * Lp + lane] : 0x10000u; };
+    u32 vnext = load_row(0);
+    int my_sym = 0;
+    for (int i = 0; i < len; ++i) {
+        const u32 v = vnext;
+        if (i + 1 < len) vnext = load_row(i + 1);
+        const u64 span = (u64)high - (u64)low + 1ull;
+        const u64 X = (((u64)value - (u64)low + 1ull) << ATTR_PRECISION) - 1ull;
+        // symbol = largest m <= max_symbol with v(m) <= floor(X / span) (0 when there is none): what the binary search returns.
+        // v <= floor(X / span)  <=>  v * span <= X: every lane tests its own entry with one multiplication, no division on the chain
+        const u32 bal = __ballot_sync(0xFFFFFFFFu, lane <= max_symbol && (u64)v * span <= X);
+        const int s = max(__popc(bal) - 1, 0);
+        const u32 c_low = __shfl_sync(0xFFFFFFFFu, v, s);
+        const u32 c_high = __shfl_sync(0xFFFFFFFFu, v, s + 1);                  // lane max_symbol + 1 holds 0x10000
+        if (lane == (i & 31)) my_sym = s;
+        high = (low - 1u) + (u32)((span * (u64)c_high) >> ATTR_PRECISION);
+        low = low + (u32)((span * (u64)c_low) >> ATTR_PRECISION);
+        for (;;) {
+            const u32 diff = low ^ high;
+            if (!(diff & 0x80000000u)) {
+                const int sh = diff ? __clz(diff) : 32;
+                const u32 bits = br.get(sh, lane);
+                if (sh == 32) { low = 0u; high = 0xFFFFFFFFu; value = bits; }
+                else { low <<= sh; high = (high << sh) | ((1u << sh) - 1u); value = (value << sh) | bits; }
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                low = (low << 1) & 0x7FFFFFFFu;
+                high = (high << 1) | 0x80000001u;
+                value -= 0x40000000u;
+                value = (value << 1) | br.get(1, lane);
+            } else {
+                break;
+            }
+        }
+        if ((i & 31) == 31 || i + 1 == len) {
+            const int i0 = i & ~31;
+            if (i0 + lane <= i) out[base + i0 + lane] = (u8)my_sym;
+        }
+    }
+}
+
+extern "C" int gpc_chunk_decode_u16(const uint16_t *cdf, const uint8_t *in, const int32_t *cnt, int64_t n, int Lp, int chunk_size,
+                                    uint8_t *sym, void *ws, size_t ws_bytes, void *stream) {
+    int rc = attr_check(n, Lp, chunk_size);
+    if (rc) return rc;
+    GPC_REQUIRE(Lp <= 257, GPC_EINVAL, "symbols are bytes");
+    if (Lp > 32) {                                       // generic path: 32-ary search over the row
+        U16Model md{cdf, Lp};
+        return attr_decode<U16Model, false, uint8_t>(md, in, cnt, n, Lp, chunk_size, sym, ws, ws_bytes, as_stream(stream));
+    }
+    cudaStream_t st = as_stream(stream);
+    AttrWs L;
+    GPC_REQUIRE(ws && ws_bytes >= attr_layout(n, chunk_size, ws, &L), GPC_ENOSPC, "workspace too small");
+    if (n == 0) return GPC_OK;
+    const int chunks = (int)((n + chunk_size - 1) / chunk_size);
+    u32 *offsets = (u32 *)L.bounds;
+    PtrLoad<u32> pl{(const u32 *)cnt};
+    rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);
+    if (rc) return rc;
+    chunk_decode_u16_kernel<0><<<cdiv(chunks, 4), 128, 0, st>>>(cdf, Lp, in, offsets, n, chunk_size, chunks, sym);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
 }

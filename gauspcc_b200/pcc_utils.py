@@ -80,7 +80,8 @@ def compress_point_cloud(
     output_path,              # Output bin file path
     channels=32,              # Network channel count
     kernel_size=5,            # Convolution kernel size
-    posQ=1                    # Quantization scale
+    posQ=1,                   # Quantization scale
+    gpu_coder_chunk=0         # extension (not in the reference): > 0 writes container version 2, see below
 ):
     """
     Compress point cloud into a bin file (reference: pcc_utils.py:24-217).
@@ -89,7 +90,13 @@ def compress_point_cloud(
     between device synchronisations, including the host range coder and excluding the checkpoint load
     and the file write, as in the reference (:78-79,188-189).  Extra key 'gpu_time': CUDA-event time
     of the device segments only.
+
+    gpu_coder_chunk > 0 (e.g. 2048): the occupancy streams are coded on the GPU in chunks of that many symbols and the file is
+    container version 2 (bitstream.py) -- smaller PCIe traffic and no host range coder on either side, but NOT readable by the
+    reference's decompress_point_cloud.  The default (0) writes the reference's own bitstream.
     """
+    if gpu_coder_chunk and not (32 <= int(gpu_coder_chunk) <= 16384):
+        raise ValueError("gpu_coder_chunk must be in 32..16384 (chunk byte counts are stored as u16)")
     os.makedirs(os.path.dirname(output_path), exist_ok=True)
     codec = _codec(ckpt_path, channels, kernel_size)
     dev = codec.dev
@@ -105,9 +112,11 @@ def compress_point_cloud(
 
     torch.cuda.synchronize(dev)
     enc_time_start = time.time()
-    base_xyz, base_occ, streams, _ = codec.encode(xyz)
+    base_xyz, base_occ, streams, _ = codec.encode(xyz, gpu_chunk=int(gpu_coder_chunk))
     torch.cuda.synchronize(dev)
     enc_time_end = time.time()
+    if gpu_coder_chunk:
+        streams = streams + [bitstream.v2_trailer(int(gpu_coder_chunk))]
 
     blob = bitstream.write_file(posQ, base_xyz, base_occ, streams)
     with open(output_path, 'wb') as f:
@@ -151,10 +160,11 @@ def decompress_point_cloud(
     with open(bin_file_path, 'rb') as f:
         blob = f.read()
     posQ, base_xyz, base_occ, streams = bitstream.read_file(blob)
+    streams, gpu_chunk = bitstream.split_v2(streams)             # container version 2 names itself in a trailing stream
 
     torch.cuda.synchronize(dev)
     dec_time_start = time.time()
-    scan = codec.decode(base_xyz, base_occ, streams, scale=float(posQ), sorted_rows=bool(sorted_output))
+    scan = codec.decode(base_xyz, base_occ, streams, scale=float(posQ), sorted_rows=bool(sorted_output), gpu_chunk=gpu_chunk)
     if not is_data_pre_quantized:
         scan = (scan - 131072) * 0.001                 # pcc_utils.py:381
     torch.cuda.synchronize(dev)

@@ -280,6 +280,14 @@ int gpc_attr_decode_gaussian(const float *mean, const float *scale, const float 
                              int64_t n, int min_value, int max_value, int chunk_size, int16_t *sym, void *ws,
                              size_t ws_bytes, void *stream);
 
+/* ---- f-3: the chunked GPU coder on the geometry codec's own streams (container version 2; NOT the torchac bitstream: one coder
+ * per chunk of chunk_size symbols instead of one per stream).  Encode: lohi as gpc_head_cdf_sym writes it; cnt / offsets / ws /
+ * gpc_attr_merge_chunks as for the attribute coder; no host synchronisation.  Decode: cdf rows as gpc_head_cdf writes them. ---- */
+int gpc_chunk_encode_lohi(const uint32_t *lohi, int64_t n, int chunk_size, int32_t *cnt, uint32_t *offsets, void *ws,
+                          size_t ws_bytes, void *stream);
+int gpc_chunk_decode_u16(const uint16_t *cdf, const uint8_t *in, const int32_t *cnt, int64_t n, int Lp, int chunk_size,
+                         uint8_t *sym, void *ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
