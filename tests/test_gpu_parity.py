@@ -603,6 +603,14 @@ def test_container_v2_gpu_chunk_coder(env, tmp_path):
         pcc_utils.compress_point_cloud(xs, ckpt, str(tmp_path / "bad" / "xyz_pcc.bin"), gpu_coder_chunk=100000)
     with pytest.raises(ValueError):                                                       # a truncated version-2 stream is an error, not a hang
         codec.decode(bx, bo, [s[:1] for s in streams], gpu_chunk=chunk)
+    # sizes around the chunk boundaries and clouds without coded levels
+    rng = np.random.default_rng(4)
+    for pts in (np.array([[5, -7, 9]], dtype=np.int32), rng.integers(-40, 40, size=(40, 3)).astype(np.int32),
+                hac_like_cloud(3000, 1, extent_log2=10), hac_like_cloud(chunk * 9 + 1, 2, extent_log2=12)):
+        for ck in (32, chunk):
+            b3, o3, s3, _ = codec.encode(torch.tensor(pts, device=codec.dev), gpu_chunk=ck)
+            got = codec.decode(b3, o3, s3, gpu_chunk=ck).cpu().numpy().astype(np.int32)
+            assert np.array_equal(np.unique(got, axis=0), np.unique(pts, axis=0))
 
 
 def test_scene_as_morton_blocks(env, tmp_path):

@@ -1,7 +1,7 @@
 """BASELINE config[4] (sample): a batch of GausPcc-1K-shaped synthetic scenes sharded BY SCENE across the GPUs of one box.
 
-    python tools/batch_scenes.py [n_scenes]                       # 1 GPU
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/batch_scenes.py [n_scenes]
+    python tools/batch_scenes.py [n_scenes] [gpu_coder_chunk]     # 1 GPU
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/batch_scenes.py [n_scenes] [gpu_coder_chunk]
 
 Each rank runs the public API (compress_point_cloud / decompress_point_cloud, host buffers, files) on its scenes
 (shard.assign_scenes, LPT by size), checks the lossless round trip, and one all_gather_into_tensor collects
@@ -18,6 +18,7 @@ from gauspcc_b200.weights import save_synthetic_checkpoint
 
 def main():
     n_scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    gpu_chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # > 0: container version 2 (GPU chunk coder, opt-in format)
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local); torch.cuda.set_device(dev)
     if world > 1:
@@ -37,7 +38,7 @@ def main():
         x = clouds[i]
         order = pcc_utils.calculate_morton_order(x)
         xs = x[order]
-        r = pcc_utils.compress_point_cloud(xs, ckpt, os.path.join(tmp, f"s{i}", "xyz_pcc.bin"))
+        r = pcc_utils.compress_point_cloud(xs, ckpt, os.path.join(tmp, f"s{i}", "xyz_pcc.bin"), gpu_coder_chunk=gpu_chunk)
         d = pcc_utils.decompress_point_cloud(r["output_path"], ckpt)
         pc = d["point_cloud"]
         ok = torch.equal(pc[pcc_utils.calculate_morton_order(pc)].cpu(), xs)
@@ -57,6 +58,7 @@ def main():
         r = res.cpu().numpy()
         assert (r[:, 0] == sizes).all()
         print(json.dumps({"config": f"{n_scenes} synthetic scenes, sizes log-uniform 100K-600K, sharded by scene", "n_gpus": world,
+                          "container": f"version 2, {gpu_chunk} symbols per chunk" if gpu_chunk else "reference bitstream",
                           "total_points": int(r[:, 0].sum()), "wall_s": round(float(tmax.item()), 3),
                           "Mpoints_s_e2e": round(float(r[:, 0].sum()) / float(tmax.item()) / 1e6, 3),
                           "mean_bpp": round(float((8 * r[:, 1] / r[:, 0]).mean()), 3), "lossless": True,
