@@ -65,18 +65,20 @@ def read_file(blob: bytes) -> Tuple[np.float16, np.ndarray, np.ndarray, List[byt
 
 
 # ---- container version 2 (opt-in): the same outer layout with ONE extra trailing stream that names the format.
-# A version-1 file has 4 * levels streams; a version-2 file has 4 * levels + 1, the last being V2_MAGIC + u32 chunk_size.  Every
+# A version-1 file has 4 * levels streams; a version-2 file has 4 * levels + 1, the last being V2_MAGIC + u32 chunk_size + u32 number
+# of coded voxels (an integrity check the reference layout has no room for: a decode that desynchronises raises).  Every
 # other stream is `u16 bytes_of_chunk[ceil(n / chunk_size)]` + the chunks' bytes, each chunk an independent range coder
 # (csrc/attr_ac.cu).  The reference cannot read it (torchac codes a stream as one coder).
 V2_MAGIC = b"GPCGC-V2"
 
 
-def v2_trailer(chunk_size: int) -> bytes:
-    return V2_MAGIC + struct.pack("<I", int(chunk_size))
+def v2_trailer(chunk_size: int, n_voxels: int) -> bytes:
+    return V2_MAGIC + struct.pack("<II", int(chunk_size), int(n_voxels))
 
 
 def split_v2(streams: List[bytes]):
-    """(streams without the trailer, chunk_size) for a version-2 stream list, (streams, 0) for version 1"""
-    if len(streams) % 4 == 1 and streams[-1][:len(V2_MAGIC)] == V2_MAGIC and len(streams[-1]) == len(V2_MAGIC) + 4:
-        return list(streams[:-1]), struct.unpack("<I", streams[-1][len(V2_MAGIC):])[0]
-    return streams, 0
+    """(streams without the trailer, chunk_size, coded voxels) for a version-2 stream list, (streams, 0, None) for version 1"""
+    if len(streams) % 4 == 1 and streams[-1][:len(V2_MAGIC)] == V2_MAGIC and len(streams[-1]) == len(V2_MAGIC) + 8:
+        chunk, n_vox = struct.unpack("<II", streams[-1][len(V2_MAGIC):])
+        return list(streams[:-1]), chunk, n_vox
+    return streams, 0, None

@@ -4,13 +4,11 @@
 // (src/ai_pcc/GausPcgc/kit/nn.py:14-16, network_ue_4stage_conv.py:18-61):
 //     y[o,:] = act( sum_{k : nbr_k(o) exists} x[nbr_k(o),:] . W[k]  (+ residual[o,:]) )
 //
-// Output-stationary: one CTA owns `TM` consecutive output rows with fp32 accumulators in shared
-// memory and walks the populated offsets k in ascending order (fixed accumulation order => the
-// encoder and the decoder produce bit-identical features).  For each k the CTA's pair list
-// (kmap.cu) gives (output row, input row); W[k] is staged through a double-buffered 4 KB shared
-// tile, the input rows are gathered with coalesced 128 B loads.
-//
-// v1 contraction: fp32 FFMA, lane = output channel, input row broadcast from shared memory.
+// This file: the mma.sync kernels (v6: one warp per tile of 8..256 rows with a cp.async gather ring, optionally the 125 offsets
+// split over the warps of a CTA; v6d: the gathered rows go straight into the MMA fragments).  They run the levels below 150 K rows
+// and are the comparison point of the tcgen05 / TMA kernel (spconv_um.cu), which runs the big dense levels; the sparse big levels
+// run spconv_sparse.cu.  All of them are output-stationary with fp32 accumulators and add a row's offsets in ascending order
+// (one fixed accumulation order => the encoder and the decoder produce bit-identical features).
 #include "common.cuh"
 
 // (The FFMA / FFMA2 kernels v1-v3, the first mma.sync kernels v4 / v5 and the experiments v7 / v8 of round 1 are gone: the mma.sync

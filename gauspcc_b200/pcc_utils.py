@@ -116,7 +116,7 @@ def compress_point_cloud(
     torch.cuda.synchronize(dev)
     enc_time_end = time.time()
     if gpu_coder_chunk:
-        streams = streams + [bitstream.v2_trailer(int(gpu_coder_chunk))]
+        streams = streams + [bitstream.v2_trailer(int(gpu_coder_chunk), int(codec.last_stats.get("n_unique", N)))]
 
     blob = bitstream.write_file(posQ, base_xyz, base_occ, streams)
     with open(output_path, 'wb') as f:
@@ -160,11 +160,14 @@ def decompress_point_cloud(
     with open(bin_file_path, 'rb') as f:
         blob = f.read()
     posQ, base_xyz, base_occ, streams = bitstream.read_file(blob)
-    streams, gpu_chunk = bitstream.split_v2(streams)             # container version 2 names itself in a trailing stream
+    streams, gpu_chunk, n_coded = bitstream.split_v2(streams)    # container version 2 names itself in a trailing stream
 
     torch.cuda.synchronize(dev)
     dec_time_start = time.time()
     scan = codec.decode(base_xyz, base_occ, streams, scale=float(posQ), sorted_rows=bool(sorted_output), gpu_chunk=gpu_chunk)
+    if n_coded is not None and scan.shape[0] != n_coded:
+        raise ValueError(f"version-2 file decodes to {scan.shape[0]} voxels, its trailer says {n_coded}: corrupt file, wrong checkpoint "
+                         "or a library whose kernels sum in another order than the writer's")
     if not is_data_pre_quantized:
         scan = (scan - 131072) * 0.001                 # pcc_utils.py:381
     torch.cuda.synchronize(dev)

@@ -598,7 +598,13 @@ def test_container_v2_gpu_chunk_coder(env, tmp_path):
     d2 = pcc_utils.decompress_point_cloud(r2["output_path"], ckpt)
     assert torch.equal(d1["point_cloud"], d2["point_cloud"])
     _, _, _, st2 = bitstream.read_file(open(r2["output_path"], "rb").read())
-    assert bitstream.split_v2(st2)[1] == 2048 and bitstream.split_v2(bitstream.read_file(open(r1["output_path"], "rb").read())[3])[1] == 0
+    assert bitstream.split_v2(st2)[1:] == (2048, 40000) and bitstream.split_v2(bitstream.read_file(open(r1["output_path"], "rb").read())[3])[1] == 0
+    # the trailer's voxel count is an integrity check: a file whose streams decode to another count raises
+    blob2 = bytearray(open(r2["output_path"], "rb").read())
+    blob2[-4:] = (39999).to_bytes(4, "little")
+    open(str(tmp_path / "v2" / "bad.bin"), "wb").write(bytes(blob2))
+    with pytest.raises(ValueError):
+        pcc_utils.decompress_point_cloud(str(tmp_path / "v2" / "bad.bin"), ckpt)
     with pytest.raises(ValueError):
         pcc_utils.compress_point_cloud(xs, ckpt, str(tmp_path / "bad" / "xyz_pcc.bin"), gpu_coder_chunk=100000)
     with pytest.raises(ValueError):                                                       # a truncated version-2 stream is an error, not a hang
