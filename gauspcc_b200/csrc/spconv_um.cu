@@ -29,6 +29,10 @@
 #include <cuda.h>
 #include "umma.cuh"
 
+#ifndef UM512_NPW
+#define UM512_NPW 3         // producer warps / gather slots of the 512-row configuration (A/B)
+#define UM512_GS 4
+#endif
 #ifndef UM_MIX_DEN
 #define UM_MIX_DEN 2         // UM_GATHER_TMA == 2: chunks with c % UM_MIX_DEN < UM_MIX_TMA go through TMA, the others through cp.async
 #define UM_MIX_TMA 1
@@ -535,8 +539,8 @@ extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t 
         return launch_spconv_um<384, 64, 6, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
     if (tile_rows == 512) {
-        if (prof) return launch_spconv_um<512, 64, 4, 3, 2, 3, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
-        return launch_spconv_um<512, 64, 4, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        if (prof) return launch_spconv_um<512, 64, UM512_GS, 3, 2, UM512_NPW, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        return launch_spconv_um<512, 64, UM512_GS, 3, 2, UM512_NPW, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
     if (prof) return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
