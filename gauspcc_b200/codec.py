@@ -618,50 +618,62 @@ class GausPcgcCodec:
                            _ptr(prob_out), self._stream())
 
     # ------------------------------------------------------------------ GPU chunk coder (container version 2)
+    @staticmethod
+    def chunk_len(n: int, chunk: int) -> int:
+        """Symbols per chunk of a version-2 stream of n symbols under the file's chunk size: the file's size, but at least 16 chunks
+        per stream where 64-symbol chunks allow -- a chunk is a serial chain on one warp, and a coarse level decoded as one or two
+        chunks would take as long as a 1M-row level.  (Every chunk costs ~4 bytes: shorter chunks on the big levels are the file's
+        choice, not this rule's.)"""
+        return max(1, min(chunk, max(64, (n + 15) // 16)))
+
     def _chunk_begin(self, stream_rows: List[int], chunk: int):
-        """Version-2 encode: ONE device array holds the (c_low, c_high) words of every stream of the scene, each stream padded to
-        whole chunks with zero words -- a zero word is the symbol [0, 0x10000): it leaves the coder's interval unchanged and costs
-        no bits, so a stream's last chunk is the stream of its real symbols.  The head kernels write their words straight into it;
-        at the end ONE launch codes all chunks of all streams at once (a chunk is one warp walking a serial chain: ten thousand of
-        them side by side take as long as one)."""
-        starts, total = [], 0
+        """Version-2 encode: ONE device array holds the (c_low, c_high) words of every stream of the scene, one after the other;
+        the head kernels write their words straight into it, and at the end ONE launch codes all chunks of all streams at once (a
+        chunk is one warp walking a serial chain: ten thousand of them side by side take as long as one)."""
+        starts, cstarts, total = [], [0], 0
         for n in stream_rows:
             starts.append(total)
-            total += (n + chunk - 1) // chunk * chunk
+            cl = self.chunk_len(n, chunk)
+            for o in range(0, n, cl):
+                cstarts.append(total + min(o + cl, n))
+            total += n
         if self._coder_arena is None or self._coder_arena.numel() < total:
-            self._coder_arena = torch.empty(int(total * 1.25) + chunk, dtype=torch.int32, device=self.dev)
-        self._coder_arena[:total].zero_()
+            self._coder_arena = torch.empty(int(total * 1.25) + 64, dtype=torch.int32, device=self.dev)
         self._coder_starts, self._coder_total, self._coder_rows = starts, total, list(stream_rows)
+        self._coder_cstarts = np.array(cstarts, dtype=np.uint32)
 
     def _chunk_slot(self, k: int) -> torch.Tensor:
         return self._coder_arena[self._coder_starts[k]:self._coder_starts[k] + self._coder_rows[k]]
 
     def _chunk_finish(self, chunk: int) -> List[bytes]:
         """code every chunk of every stream in one launch, bring counts and bytes to the host in one staging copy each"""
-        total = self._coder_total
-        if total == 0:
-            return []
-        chunks = total // chunk
+        chunks = int(self._coder_cstarts.shape[0]) - 1
+        if chunks <= 0:
+            return [b""] * len(self._coder_rows)
+        cstarts = torch.from_numpy(self._coder_cstarts.view(np.int32)).to(self.dev)
         cnt = self._empty((chunks,), torch.int32)
         offs = self._empty((chunks + 1,), torch.int32)
-        ws_b = self.lib.gpc_attr_workspace_bytes(total, chunk)
+        ws_b = self.lib.gpc_chunk_workspace_bytes(chunks, chunk)
         ws = self._ws(ws_b)
-        self._call("gpc_chunk_encode_lohi", _ptr(self._coder_arena), total, chunk, _ptr(cnt), _ptr(offs), _ptr(ws), ws_b, self._stream())
+        self._call("gpc_chunk_encode_lohi", _ptr(self._coder_arena), _ptr(cstarts), chunks, chunk, _ptr(cnt), _ptr(offs), _ptr(ws), ws_b,
+                   self._stream())
         cnt_h = cnt.cpu().numpy()                                               # synchronises; offsets on the host from the counts
         if cnt_h.size and int(cnt_h.max()) > 0xFFFF:
             raise ValueError("chunk too long for the u16 byte counts of container version 2")
         offs_h = np.concatenate([[0], np.cumsum(cnt_h, dtype=np.int64)])
         nbytes = int(offs_h[-1])
         out = self._empty((nbytes + 64,), torch.uint8)
-        self._call("gpc_attr_merge_chunks", _ptr(ws), total, chunk, _ptr(offs), _ptr(out), self._stream())
+        self._call("gpc_chunk_merge", _ptr(ws), chunks, chunk, _ptr(offs), _ptr(out), self._stream())
         pin = self._pin(nbytes + 64)
         pin[:nbytes].copy_(out[:nbytes], non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         host = pin.numpy()
-        streams = []
-        for start, n in zip(self._coder_starts, self._coder_rows):
-            c0, c1 = start // chunk, start // chunk + (n + chunk - 1) // chunk
+        streams, c0 = [], 0
+        for n in self._coder_rows:
+            cl = self.chunk_len(n, chunk)
+            c1 = c0 + (n + cl - 1) // cl
             streams.append(cnt_h[c0:c1].astype("<u2").tobytes() + host[int(offs_h[c0]):int(offs_h[c1])].tobytes())
+            c0 = c1
         return streams
 
     def _chunk_upload(self, streams: List[bytes]):
@@ -680,6 +692,7 @@ class GausPcgcCodec:
         return dev, offs
 
     def _chunk_decode(self, cdf_d: torch.Tensor, stream: bytes, dev_bytes: torch.Tensor, off: int, n: int, Lp: int, chunk: int) -> torch.Tensor:
+        chunk = self.chunk_len(n, chunk)
         chunks = (n + chunk - 1) // chunk
         if len(stream) < 2 * chunks:
             raise ValueError("truncated version-2 stream")

@@ -131,12 +131,13 @@ struct LohiLoad {                                    // c_low | c_high << 16, c_
 template <typename Load>
 __global__ void __launch_bounds__(128) attr_encode_chunks_kernel(Load bounds, i64 n, int chunk_size, int chunks,
                                                                 u8 *__restrict__ cache, i64 cap, i32 *__restrict__ cnt,
-                                                                int *__restrict__ status) {
+                                                                int *__restrict__ status, const u32 *__restrict__ starts = nullptr) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= chunks) return;
-    const i64 base = (i64)w * chunk_size;
-    const int len = (int)min((i64)chunk_size, n - base);
+    // chunks of chunk_size symbols, or (starts given) chunk w = symbols [starts[w], starts[w + 1]) of at most chunk_size symbols
+    const i64 base = starts ? (i64)starts[w] : (i64)w * chunk_size;
+    const int len = starts ? (int)(starts[w + 1] - starts[w]) : (int)min((i64)chunk_size, n - base);
     BitWriter bw{cache + (i64)w * cap, cap, 0, 0ull, 0, false};
     const bool store = lane == 0;
     u32 low = 0u, high = 0xFFFFFFFFu;
@@ -458,20 +459,44 @@ extern "C" int gpc_attr_decode_gaussian(const float *mean, const float *scale, c
 // ---- the same chunked coder on the geometry codec's own symbols (container version 2): the occupancy streams of a
 // level coded on the GPU in chunks instead of by one serial host coder per stream.  Not the reference's bitstream (torchac codes a
 // stream as ONE coder): an opt-in container next to the drop-in one.
-extern "C" int gpc_chunk_encode_lohi(const uint32_t *lohi, int64_t n, int chunk_size, int32_t *cnt, uint32_t *offsets, void *ws,
-                                     size_t ws_bytes, void *stream) {
-    int rc = attr_check(n, 3, chunk_size);
-    if (rc) return rc;
+// chunks: chunk w = symbols [starts[w], starts[w + 1]) of lohi, at most max_chunk symbols each (the streams of a scene one after
+// the other, every stream cut into chunks of its own length).  cnt[chunks], offsets[chunks + 1]; no host synchronisation.
+static size_t chunk_var_layout(int chunks, int max_chunk, void *ws, AttrWs *L) {
+    char *b = (char *)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+    L->status = (int *)take(256);
+    L->bounds = nullptr;
+    L->cap = (i64)max_chunk * 4;
+    L->cache = (u8 *)take((size_t)chunks * L->cap);
+    L->scan_ws = take(scan_workspace_bytes<u32>(chunks + 1) + 1024);
+    return off;
+}
+extern "C" size_t gpc_chunk_workspace_bytes(int chunks, int max_chunk) {
+    AttrWs L;
+    if (chunks < 0 || max_chunk < 1) return 0;
+    return chunk_var_layout(chunks, max_chunk, nullptr, &L);
+}
+extern "C" int gpc_chunk_encode_lohi(const uint32_t *lohi, const uint32_t *starts, int chunks, int max_chunk, int32_t *cnt,
+                                     uint32_t *offsets, void *ws, size_t ws_bytes, void *stream) {
+    GPC_REQUIRE(chunks >= 0 && max_chunk >= 1 && max_chunk <= (1 << 24), GPC_EINVAL, "bad argument");
     cudaStream_t st = as_stream(stream);
     AttrWs L;
-    GPC_REQUIRE(ws && ws_bytes >= attr_layout(n, chunk_size, ws, &L), GPC_ENOSPC, "workspace too small");
-    const int chunks = (int)((n + chunk_size - 1) / chunk_size);
+    GPC_REQUIRE(ws && ws_bytes >= chunk_var_layout(chunks, max_chunk, ws, &L), GPC_ENOSPC, "workspace too small");
     GPC_CUDA_CHECK(cudaMemsetAsync(L.status, 0, 4, st));
-    if (n == 0) { GPC_CUDA_CHECK(cudaMemsetAsync(offsets, 0, 4, st)); return GPC_OK; }
-    attr_encode_chunks_kernel<LohiLoad><<<cdiv(chunks, 4), 128, 0, st>>>(LohiLoad{lohi}, n, chunk_size, chunks, L.cache, L.cap, cnt, L.status);
+    if (chunks == 0) { GPC_CUDA_CHECK(cudaMemsetAsync(offsets, 0, 4, st)); return GPC_OK; }
+    attr_encode_chunks_kernel<LohiLoad><<<cdiv(chunks, 4), 128, 0, st>>>(LohiLoad{lohi}, 0, max_chunk, chunks, L.cache, L.cap, cnt, L.status, starts);
     GPC_LAUNCH_CHECK();
     PtrLoad<u32> pl{(const u32 *)cnt};
-    return device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);     // no host synchronisation
+    return device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);
+}
+extern "C" int gpc_chunk_merge(const void *ws, int chunks, int max_chunk, const uint32_t *offsets, uint8_t *out, void *stream) {
+    AttrWs L;
+    chunk_var_layout(chunks, max_chunk, (void *)ws, &L);
+    if (chunks <= 0) return GPC_OK;
+    attr_merge_kernel<<<chunks, 256, 0, as_stream(stream)>>>(L.cache, L.cap, offsets, out);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
 }
 
 // Decoder of the geometry streams: alphabets of 2 / 2 / 4 / 16 symbols, so a whole CDF row (Lp <= 32 entries) is ONE coalesced load,

@@ -577,13 +577,15 @@ def test_container_v2_gpu_chunk_coder(env, tmp_path):
         sym = O.split_symbols(occ)[i].astype(np.int16)
         cdf = aux["cdfs"][k].cpu().numpy().view(np.uint16)
         n = sym.shape[0]
-        chunks = (n + chunk - 1) // chunk
+        cl = codec.chunk_len(n, chunk)                                                    # short streams take shorter chunks
+        assert cl == max(1, min(chunk, max(64, (n + 15) // 16)))
+        chunks = (n + cl - 1) // cl
         cnt = np.frombuffer(streams[k], dtype="<u2", count=chunks).astype(np.int64)
         body = streams[k][2 * chunks:]
         assert cnt.sum() == len(body)
         pos = 0
         for c in range(chunks):
-            want = O.ac_encode(cdf[c * chunk:(c + 1) * chunk], sym[c * chunk:(c + 1) * chunk])
+            want = O.ac_encode(cdf[c * cl:(c + 1) * cl], sym[c * cl:(c + 1) * cl])
             assert body[pos:pos + cnt[c]] == want, (k, c)
             pos += cnt[c]
     dec = codec.decode(bx, bo, streams, gpu_chunk=chunk)
