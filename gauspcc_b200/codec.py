@@ -13,6 +13,7 @@ HBM layout of one octree level (rows in ascending key order == the reference's (
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import queue
@@ -135,6 +136,8 @@ class GausPcgcCodec:
         self.wave_streams = True
         self._wave_side: Optional[list] = None
         self._wave_buf: Optional[torch.Tensor] = None
+        self.enc_overlap = True                       # encoder: coarse levels on a side stream beside the big levels' kernels
+        self._enc_side = None
         self._coder_arena = None                      # (c_low, c_high) words of all streams of a scene (container version 2)
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
         self.debug_dec_cdfs: Optional[dict] = None    # tests: (level, stage) -> CDF rows the stage-by-stage decoder computed
@@ -735,6 +738,33 @@ class GausPcgcCodec:
                                             sym_out.ctypes.data_as(C.c_void_p)), "gpc_ac_decode_h")
 
     # ------------------------------------------------------------------ encode
+    def _encode_level(self, d: int, parent: Level, gt: Level, collect: bool, download: bool, gpu_chunk: int, aux, carve, level_futs):
+        """one octree level of the encoder on the current stream: features, four stages, (c_low, c_high) words on their way to the coder"""
+        child, u = self.level_features(parent, gt.n, child_kmap=gt.kmap)      # same coordinate set, same row order
+        if collect:
+            aux["child_keys"][d] = child.keys
+        level_jobs = []
+        for i in range(4):
+            A = W.STAGE_ALPHABETS[i]
+            cdf_d = self._empty((gt.n, A + 1), torch.int16) if collect else None
+            prob_d = self._empty((gt.n, A), torch.float32) if collect else None
+            lohi_d = self._chunk_slot(4 * d + i) if (download and gpu_chunk) else self._empty((gt.n,), torch.int32)
+            self.stage_cdf(u, gt.occ, i, child.kmap, cdf_d, prob_d, lohi_out=lohi_d)
+            if download and gpu_chunk:
+                pass                                                        # coded with all other streams at the end (_chunk_finish)
+            elif download:
+                lohi_h = carve(gt.n * 4, torch.int32, (gt.n,))
+                lohi_h.copy_(lohi_d, non_blocking=True)
+                level_jobs.append(lohi_h)
+            if collect:
+                aux["probs"][4 * d + i] = prob_d
+                aux["cdfs"][4 * d + i] = cdf_d
+        if download and not gpu_chunk:
+            ready = torch.cuda.Event(blocking=True)          # the coder threads sleep on it instead of spinning
+            ready.record(torch.cuda.current_stream(self.dev))
+            # host range coding of this level overlaps the GPU work of the coarser levels
+            level_futs[d] = [self.pool.submit(self._ac_encode_lohi, h.numpy().view(np.uint32), ready) for h in level_jobs]
+
     def encode(self, xyz: torch.Tensor, collect: bool = False, download: bool = True, gpu_chunk: int = 0):
         """[N,3] CUDA float32/int32 voxel indices -> (base_xyz int32 [n0,3], base_occ u8 [n0], streams, aux).
 
@@ -797,32 +827,25 @@ class GausPcgcCodec:
             self._chunk_begin([levels[k // 4 + 1].n for k in range(4 * L)], gpu_chunk)
         if collect:
             aux["child_keys"], aux["probs"], aux["cdfs"] = [None] * L, [None] * (4 * L), [None] * (4 * L)
+        # The coarse levels (below um_min_rows rows: launches of 15-180 us that leave most SMs idle) go to a side stream, beside the
+        # big levels' kernels -- every level of the encoder is independent work.  Not while bench.py's per-stage profile is on (its
+        # event pairs assume one stream).
+        side = None
+        if self.enc_overlap and self.conv_profile is None and not collect and L > 1:
+            if self._enc_side is None:
+                self._enc_side = torch.cuda.Stream(self.dev)
+            side = self._enc_side
+            side.wait_stream(torch.cuda.current_stream(self.dev))              # pyramid and kernel maps are complete
+        main_h = self._stream_h
         for d in range(L - 1, -1, -1):
             parent, gt = levels[d], levels[d + 1]
-            child, u = self.level_features(parent, gt.n, child_kmap=gt.kmap)      # same coordinate set, same row order
-            if collect:
-                aux["child_keys"][d] = child.keys
-            level_jobs = []
-            for i in range(4):
-                A = W.STAGE_ALPHABETS[i]
-                cdf_d = self._empty((gt.n, A + 1), torch.int16) if collect else None
-                prob_d = self._empty((gt.n, A), torch.float32) if collect else None
-                lohi_d = self._chunk_slot(4 * d + i) if (download and gpu_chunk) else self._empty((gt.n,), torch.int32)
-                self.stage_cdf(u, gt.occ, i, child.kmap, cdf_d, prob_d, lohi_out=lohi_d)
-                if download and gpu_chunk:
-                    pass                                                        # coded with all other streams at the end (_chunk_finish)
-                elif download:
-                    lohi_h = carve(gt.n * 4, torch.int32, (gt.n,))
-                    lohi_h.copy_(lohi_d, non_blocking=True)
-                    level_jobs.append(lohi_h)
-                if collect:
-                    aux["probs"][4 * d + i] = prob_d
-                    aux["cdfs"][4 * d + i] = cdf_d
-            if download and not gpu_chunk:
-                ready = torch.cuda.Event(blocking=True)          # the coder threads sleep on it instead of spinning
-                ready.record(torch.cuda.current_stream(self.dev))
-                # host range coding of this level overlaps the GPU work of the coarser levels
-                level_futs[d] = [self.pool.submit(self._ac_encode_lohi, h.numpy().view(np.uint32), ready) for h in level_jobs]
+            on_side = side is not None and gt.n < self.um_min_rows
+            with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
+                self._stream_h = side.cuda_stream if on_side else main_h
+                self._encode_level(d, parent, gt, collect, download, gpu_chunk, aux, carve, level_futs)
+        self._stream_h = main_h
+        if side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(side)
         futs = [f for lf in level_futs for f in lf]            # stream order of the container: level-major coarse -> fine
         base = levels[0]
         base_xyz = self._empty((base.n, 3), torch.int32)
