@@ -136,8 +136,8 @@ class GausPcgcCodec:
         self.wave_streams = True
         self._wave_side: Optional[list] = None
         self._wave_buf: Optional[torch.Tensor] = None
-        self.enc_overlap = True                       # encoder: coarse levels on a side stream beside the big levels' kernels
-        self._enc_side = None
+        self.enc_overlap = 1                          # encoder: side streams; the levels (independent work) take main and these in turn (0 / 1 / 2-6 side streams: 61.8 / 56.4 / 56.5-57.8 ms per 1M-anchor encode)
+        self._enc_sides = []
         self._coder_arena = None                      # (c_low, c_high) words of all streams of a scene (container version 2)
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
         self.debug_dec_cdfs: Optional[dict] = None    # tests: (level, stage) -> CDF rows the stage-by-stage decoder computed
@@ -827,25 +827,31 @@ class GausPcgcCodec:
             self._chunk_begin([levels[k // 4 + 1].n for k in range(4 * L)], gpu_chunk)
         if collect:
             aux["child_keys"], aux["probs"], aux["cdfs"] = [None] * L, [None] * (4 * L), [None] * (4 * L)
-        # The coarse levels (below um_min_rows rows: launches of 15-180 us that leave most SMs idle) go to a side stream, beside the
-        # big levels' kernels -- every level of the encoder is independent work.  Not while bench.py's per-stage profile is on (its
-        # event pairs assume one stream).
-        side = None
+        # Every level of the encoder is independent work: the levels are spread over the main stream and enc_overlap side streams,
+        # so that one level's launch tails, pipeline ramps and small kernels (embeddings, heads, the 15-180 us launches of the coarse
+        # levels) run beside another level's convs.  Not while bench.py's per-stage profile is on (its event pairs assume one stream).
+        sides = []
+        main = torch.cuda.current_stream(self.dev)
         if self.enc_overlap and self.conv_profile is None and not collect and L > 1:
-            if self._enc_side is None:
-                self._enc_side = torch.cuda.Stream(self.dev)
-            side = self._enc_side
-            side.wait_stream(torch.cuda.current_stream(self.dev))              # pyramid and kernel maps are complete
+            while len(self._enc_sides) < self.enc_overlap:
+                self._enc_sides.append(torch.cuda.Stream(self.dev))
+            sides = self._enc_sides[:self.enc_overlap]
+            for st in sides:
+                st.wait_stream(main)                                           # pyramid and kernel maps are complete
         main_h = self._stream_h
         for d in range(L - 1, -1, -1):
             parent, gt = levels[d], levels[d + 1]
-            on_side = side is not None and gt.n < self.um_min_rows
-            with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
-                self._stream_h = side.cuda_stream if on_side else main_h
+            # big levels take main and the side streams in turn; the coarse levels all go to the last side stream
+            st = None
+            if sides:
+                slot = (L - 1 - d) % (len(sides) + 1) if gt.n >= self.um_min_rows else len(sides)
+                st = sides[slot - 1] if slot else None
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                self._stream_h = st.cuda_stream if st is not None else main_h
                 self._encode_level(d, parent, gt, collect, download, gpu_chunk, aux, carve, level_futs)
         self._stream_h = main_h
-        if side is not None:
-            torch.cuda.current_stream(self.dev).wait_stream(side)
+        for st in sides:
+            main.wait_stream(st)
         futs = [f for lf in level_futs for f in lf]            # stream order of the container: level-major coarse -> fine
         base = levels[0]
         base_xyz = self._empty((base.n, 3), torch.int32)
