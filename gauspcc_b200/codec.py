@@ -138,6 +138,8 @@ class GausPcgcCodec:
         self._wave_buf: Optional[torch.Tensor] = None
         self.enc_overlap = 1                          # encoder: side streams; the levels (independent work) take main and these in turn (0 / 1 / 2-6 side streams: 61.8 / 56.4 / 56.5-57.8 ms per 1M-anchor encode)
         self._enc_sides = []
+        self.dec_overlap = True                       # decoder: children + their kernel map on a side stream beside the prior stack
+        self._dec_side = None
         self._coder_arena = None                      # (c_low, c_high) words of all streams of a scene (container version 2)
         self.wave_log: Optional[list] = None          # tools/wave_times.py: per-level record of the wavefront
         self.debug_dec_cdfs: Optional[dict] = None    # tests: (level, stage) -> CDF rows the stage-by-stage decoder computed
@@ -575,12 +577,34 @@ class GausPcgcCodec:
         with self._stage("embed", parent.n * 129):
             self._call("gpc_embed_rows", _ptr(parent.occ), parent.n, _ptr(self.w.prior_emb), None if pum else _ptr(f), _ptr(f) if pum else None,
                        self._stream())
-        f = self.res_stack(f, W.PRIOR_CONVS, parent.kmap)            # fp32 rows (the children gather them)
-        with self._stage("expand", parent.n * 33 + n_child * 12):
-            ck, cp = self.expand(parent, n_child)
-        if child_kmap is None:
-            with self._stage("kmap", self._kmap_bytes(n_child)):
+        if child_kmap is None and self.dec_overlap and self.conv_profile is None and n_child >= 20_000:
+            # decoder: the children and their kernel map depend on the parents' occupancy only, not on the prior features --
+            # they are built on a side stream (incl. the host round trip of the pair counts) while the prior stack runs
+            main = torch.cuda.current_stream(self.dev)
+            ready = torch.cuda.Event()
+            ready.record(main)                                       # parent.keys / parent.occ are complete
+            f = self.res_stack(f, W.PRIOR_CONVS, parent.kmap)        # enqueued on main; the host goes on
+            if self._dec_side is None:
+                self._dec_side = torch.cuda.Stream(self.dev)
+            side, main_h = self._dec_side, self._stream_h
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                self._stream_h = side.cuda_stream
+                ck, cp = self.expand(parent, n_child)
                 child_kmap = self.build_kmap(ck)
+            self._stream_h = main_h
+            main.wait_stream(side)
+            for t in (ck, cp, child_kmap.seg, child_kmap.pairs, child_kmap.pair_nbr, child_kmap.pair_off, child_kmap.rowptr,
+                      child_kmap.contrib, child_kmap.tile_order):
+                if t is not None:
+                    t.record_stream(main)                            # allocated under the side stream, used on main from here on
+        else:
+            f = self.res_stack(f, W.PRIOR_CONVS, parent.kmap)        # fp32 rows (the children gather them)
+            with self._stage("expand", parent.n * 33 + n_child * 12):
+                ck, cp = self.expand(parent, n_child)
+            if child_kmap is None:
+                with self._stage("kmap", self._kmap_bytes(n_child)):
+                    child_kmap = self.build_kmap(ck)
         child = Level(ck, None, n_child, child_kmap)
         cum = bool(child.kmap.um_rows)
         u0 = self._empty((n_child, 32), torch.int32 if cum else torch.float32)
