@@ -364,8 +364,9 @@ def main():
                                 "share_of_profiled_step": per_stage[0]["share"],
                                 "tflops_effective_fp32": round(dom["flops"] / (dom["ms"] / 1e3) / 1e12, 2),
                                 "note": "measured in two separate profiled steps (one CUDA-event pair per group of convs on a level) after the timed "
-                                        "region; the kernel is bound by its warp-specialised pipeline (hand-offs and the MMA-issue warp), not by HBM: "
-                                        "profiles/r02_conv_um.md"}
+                                        "region, on ONE stream: the profile switches off the overlap of independent levels / kernel-map builds "
+                                        "on side streams that the timed step uses, so per_stage sums to more than ms_per_step; the kernel is bound "
+                                        "by its warp-specialised pipeline (hand-off latency between the roles), not by HBM: profiles/r02_conv_um.md"}
             line["per_stage"] = per_stage
         if e2e:
             line["e2e"] = e2e
