@@ -199,10 +199,10 @@ __global__ void __launch_bounds__(128) sp_straggler_kernel(const float *__restri
 }
 
 // ---------------------------------------------------------------- kernel 2: dense centre product + the rows' contributions
-constexpr int SP_ROWS = 64;        // rows per warp
+constexpr int SP_ROWS = 32;        // rows per warp (64 rows and 5 CTAs per SM: 0.329 / 0.176 / 0.144 ms on the three sparse levels; 32 rows and 8 CTAs: 0.295 / 0.147 / 0.115)
 constexpr int SP_ACC = 36;
 
-__global__ void __launch_bounds__(128) sp_centre_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
+__global__ void __launch_bounds__(128, 8) sp_centre_kernel(const float *__restrict__ x, const uint4 *__restrict__ Wa,
                                                         const u32 *__restrict__ rowptr, const float *__restrict__ contrib, i64 row0, i64 n,
                                                         const float *__restrict__ residual, int flags, float *__restrict__ y) {
     __shared__ float acc_all[4][SP_ROWS][SP_ACC];
