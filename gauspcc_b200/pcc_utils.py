@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import time
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch

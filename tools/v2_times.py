@@ -1,9 +1,9 @@
 """Where container version 2 (GPU chunk coder) spends its time: encode / decode wall and CUDA-event times per phase, chunk kernels
 timed alone on the largest level.    python tools/v2_times.py [n_points] [chunk]"""
 import os, sys, time
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gauspcc_b200.codec import DeviceWeights, GausPcgcCodec, _ptr
+from gauspcc_b200.codec import DeviceWeights, GausPcgcCodec
 from gauspcc_b200.pcc_utils import calculate_morton_order
 from gauspcc_b200.synth import hac_like_cloud
 from gauspcc_b200.weights import make_synthetic_state_dict
