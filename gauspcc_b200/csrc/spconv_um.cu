@@ -33,6 +33,11 @@
 #define UM512_NPW 3         // producer warps / gather slots of the 512-row configuration (A/B)
 #define UM512_GS 4
 #endif
+#ifndef UM512_NMAX
+#define UM512_NMAX 64       // pairs per chunk of the 512-row configuration; 96 (with GS 3, DS 2, NEW 6) halves the chunks of cells of 65..96 pairs (A/B)
+#define UM512_DS 3
+#define UM512_NEW 8
+#endif
 #ifndef UM_MIX_DEN
 #define UM_MIX_DEN 2         // UM_GATHER_TMA == 2: chunks with c % UM_MIX_DEN < UM_MIX_TMA go through TMA, the others through cp.async
 #define UM_MIX_TMA 1
@@ -58,7 +63,7 @@ struct UmSmem {
     __align__(16) u32 idx[NPW][4][NMAX];               // per producer: input rows of the pairs of its next chunks
     u32 seg[GPC_K3 + 3];
     u32 cstart[GPC_K3 + 3];
-    u32 tab[GPC_K3 * (TM / NMAX) + 8];                 // chunk -> k | j << 8 | len << 12 | last chunk of its offset << 20 | offset ordinal << 24
+    u32 tab[GPC_K3 * ((TM + NMAX - 1) / NMAX) + 8];                 // chunk -> k | j << 8 | len << 12 | last chunk of its offset << 20 | offset ordinal << 24
     u32 wcnt[4];
     __align__(8) u64 full_g[GS];
     u64 empty_g[GS];
@@ -121,7 +126,7 @@ spconv_um_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     constexpr u32 A_COL = DS * NMAX;             // first weight column of tensor memory
     static_assert(A_COL + WS * 32 <= TCOLS, "TMEM columns");
     static_assert(NMAX == 16 * NEW || NMAX == 8 * NEW, "an epilogue warp takes 8 or 16 columns of a chunk");
-    static_assert(NPW >= 1 && (NMAX == 64 || NMAX == 128), "shape");
+    static_assert(NPW >= 1 && (NMAX == 64 || NMAX == 96 || NMAX == 128), "shape");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     typedef UmSmem<TM, NMAX, GS, DS, WS, NPW> Smem;
     Smem &s = *reinterpret_cast<Smem *>(smem_raw);
@@ -515,7 +520,7 @@ extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t 
     CUtensorMap tmap;                                            // [n rows][64 bf16], box = one chunk of consecutive rows (the centre offset)
     const cuuint64_t gdim[2] = {64, (cuuint64_t)n};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {64, (cuuint32_t)(tile_rows == 1024 ? 128 : 64)};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(tile_rows == 1024 ? 128 : (tile_rows == 512 ? UM512_NMAX : 64))};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(xs), gdim, gstride, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -539,8 +544,8 @@ extern "C" int gpc_spconv_fwd_um(const void *xs, const void *Wp, const uint32_t 
         return launch_spconv_um<384, 64, 6, 3, 2, 3, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
     if (tile_rows == 512) {
-        if (prof) return launch_spconv_um<512, 64, UM512_GS, 3, 2, UM512_NPW, 8, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
-        return launch_spconv_um<512, 64, UM512_GS, 3, 2, UM512_NPW, 8, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        if (prof) return launch_spconv_um<512, UM512_NMAX, UM512_GS, UM512_DS, 2, UM512_NPW, UM512_NEW, 256, 2, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
+        return launch_spconv_um<512, UM512_NMAX, UM512_GS, UM512_DS, 2, UM512_NPW, UM512_NEW, 256, 2>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     }
     if (prof) return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1, true>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
     return launch_spconv_um<1024, 128, 4, 3, 4, 4, 8, 512, 1>(tmap, tmap_g, xs, Wp, seg, pair_nbr, pair_off, n, tile0, tiles, order, residual, flags, y, ys, st);
