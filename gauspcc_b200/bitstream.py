@@ -68,7 +68,7 @@ def read_file(blob: bytes) -> Tuple[np.float16, np.ndarray, np.ndarray, List[byt
 # A version-1 file has 4 * levels streams; a version-2 file has 4 * levels + 1, the last being V2_MAGIC + u32 chunk_size + u32 number
 # of coded voxels (an integrity check the reference layout has no room for: a decode that desynchronises raises).  Every
 # other stream is `u16 bytes_of_chunk[chunks]` + the chunks' bytes, each chunk an independent range coder (csrc/attr_ac.cu) over
-# chunk_len(n, chunk_size) = min(chunk_size, max(64, ceil(n / 16))) symbols of the stream's n (GausPcgcCodec.chunk_len: short
+# chunk_len(n, chunk_size) = min(chunk_size, max(64, ceil(n / 64))) symbols of the stream's n (GausPcgcCodec.chunk_len: short
 # streams take shorter chunks so that a small level is not a handful of long serial chains).  The reference cannot read it (torchac codes a stream as one coder).
 V2_MAGIC = b"GPCGC-V2"
 

@@ -647,11 +647,11 @@ class GausPcgcCodec:
     # ------------------------------------------------------------------ GPU chunk coder (container version 2)
     @staticmethod
     def chunk_len(n: int, chunk: int) -> int:
-        """Symbols per chunk of a version-2 stream of n symbols under the file's chunk size: the file's size, but at least 16 chunks
+        """Symbols per chunk of a version-2 stream of n symbols under the file's chunk size: the file's size, but at least 64 chunks
         per stream where 64-symbol chunks allow -- a chunk is a serial chain on one warp, and a coarse level decoded as one or two
         chunks would take as long as a 1M-row level.  (Every chunk costs ~4 bytes: shorter chunks on the big levels are the file's
         choice, not this rule's.)"""
-        return max(1, min(chunk, max(64, (n + 15) // 16)))
+        return max(1, min(chunk, max(64, (n + 63) // 64)))
 
     def _chunk_begin(self, stream_rows: List[int], chunk: int):
         """Version-2 encode: ONE device array holds the (c_low, c_high) words of every stream of the scene, one after the other;

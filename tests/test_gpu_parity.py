@@ -578,7 +578,7 @@ def test_container_v2_gpu_chunk_coder(env, tmp_path):
         cdf = aux["cdfs"][k].cpu().numpy().view(np.uint16)
         n = sym.shape[0]
         cl = codec.chunk_len(n, chunk)                                                    # short streams take shorter chunks
-        assert cl == max(1, min(chunk, max(64, (n + 15) // 16)))
+        assert cl == max(1, min(chunk, max(64, (n + 63) // 64)))
         chunks = (n + cl - 1) // cl
         cnt = np.frombuffer(streams[k], dtype="<u2", count=chunks).astype(np.int64)
         body = streams[k][2 * chunks:]
