@@ -704,18 +704,22 @@ class GausPcgcCodec:
         return streams
 
     def _chunk_upload(self, streams: List[bytes]):
-        """all version-2 streams of a file -> device in ONE staging copy (a 1M-anchor scene is ~9 MB); per stream its offset"""
+        """all version-2 streams of a file -> device in ONE staging copy (a 1M-anchor scene is ~9 MB); per stream its offset.
+        Behind them room for the chunks' byte offsets, which the levels fill in as their sizes become known."""
+        torch.cuda.current_stream(self.dev).synchronize()        # nothing of an earlier call still reads the staging buffer
         offs, total = [], 0
         for sb in streams:
             offs.append(total)
             total += (len(sb) + 255) // 256 * 256
-        pin = self._pin(total + 256)
+        room = 2 * sum(len(sb) for sb in streams) + 64 * len(streams) + 4096          # a chunk has a 2-byte count in its stream: <= len / 2 chunks, 4 B each
+        pin = self._pin(total + room)
         host = pin.numpy()
         for o, sb in zip(offs, streams):
             host[o:o + len(sb)] = np.frombuffer(sb, dtype=np.uint8)
-        dev = torch.empty(total + 256, dtype=torch.uint8, device=self.dev)
+        dev = torch.empty(total + room, dtype=torch.uint8, device=self.dev)
         dev[:total].copy_(pin[:total], non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()        # the staging buffer is free again (the GPU is idle here anyway)
+        self._v2_cursor, self._v2_end = total, total + room
         return dev, offs
 
     def _chunk_decode(self, cdf_d: torch.Tensor, stream: bytes, dev_bytes: torch.Tensor, off: int, n: int, Lp: int, chunk: int) -> torch.Tensor:
@@ -724,14 +728,21 @@ class GausPcgcCodec:
         if len(stream) < 2 * chunks:
             raise ValueError("truncated version-2 stream")
         cnt_h = np.frombuffer(stream, dtype="<u2", count=chunks)
-        if int(cnt_h.astype(np.int64).sum()) != len(stream) - 2 * chunks:
+        offs_h = np.zeros(chunks + 1, dtype=np.uint32)
+        np.cumsum(cnt_h, dtype=np.uint32, out=offs_h[1:])
+        if int(offs_h[-1]) != len(stream) - 2 * chunks:
             raise ValueError("corrupt version-2 stream (chunk byte counts)")
-        cnt = dev_bytes[off:off + 2 * chunks].view(torch.int16).to(torch.int32) & 0xFFFF          # u16 counts, widened on the device
+        # the chunks' byte offsets: host prefix sums, into their own (never reused) piece of the staging buffer and the device array
+        a = (self._v2_cursor + 15) // 16 * 16
+        b = a + 4 * (chunks + 1)
+        if b > self._v2_end:
+            raise ValueError("corrupt version-2 file (more chunks than its streams can hold)")
+        self._v2_cursor = b
+        self._pinned.numpy()[a:b] = offs_h.view(np.uint8)
+        dev_bytes[a:b].copy_(self._pinned[a:b], non_blocking=True)
         sym = self._empty((n,), torch.uint8)
-        ws_b = self.lib.gpc_attr_workspace_bytes(n, chunk)
-        ws = self._ws(ws_b)
-        self._call("gpc_chunk_decode_u16", _ptr(cdf_d), C.c_void_p(dev_bytes.data_ptr() + off + 2 * chunks), _ptr(cnt), n, Lp, chunk,
-                   _ptr(sym), _ptr(ws), ws_b, self._stream())
+        self._call("gpc_chunk_decode_u16", _ptr(cdf_d), C.c_void_p(dev_bytes.data_ptr() + off + 2 * chunks), C.c_void_p(dev_bytes.data_ptr() + a),
+                   n, Lp, chunk, _ptr(sym), self._stream())
         return sym
 
     # ------------------------------------------------------------------ host range coder

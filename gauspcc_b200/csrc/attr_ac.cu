@@ -558,25 +558,15 @@ __global__ void __launch_bounds__(128) chunk_decode_u16_kernel(const u16 *__rest
     }
 }
 
-extern "C" int gpc_chunk_decode_u16(const uint16_t *cdf, const uint8_t *in, const int32_t *cnt, int64_t n, int Lp, int chunk_size,
-                                    uint8_t *sym, void *ws, size_t ws_bytes, void *stream) {
+// offsets: device u32[chunks + 1], first byte of every chunk in `in` (the caller's prefix sums of the chunks' byte counts)
+extern "C" int gpc_chunk_decode_u16(const uint16_t *cdf, const uint8_t *in, const uint32_t *offsets, int64_t n, int Lp, int chunk_size,
+                                    uint8_t *sym, void *stream) {
     int rc = attr_check(n, Lp, chunk_size);
     if (rc) return rc;
-    GPC_REQUIRE(Lp <= 257, GPC_EINVAL, "symbols are bytes");
-    if (Lp > 32) {                                       // generic path: 32-ary search over the row
-        U16Model md{cdf, Lp};
-        return attr_decode<U16Model, false, uint8_t>(md, in, cnt, n, Lp, chunk_size, sym, ws, ws_bytes, as_stream(stream));
-    }
-    cudaStream_t st = as_stream(stream);
-    AttrWs L;
-    GPC_REQUIRE(ws && ws_bytes >= attr_layout(n, chunk_size, ws, &L), GPC_ENOSPC, "workspace too small");
+    GPC_REQUIRE(Lp <= 32, GPC_EINVAL, "a CDF row must fit one warp load (Lp <= 32)");
     if (n == 0) return GPC_OK;
     const int chunks = (int)((n + chunk_size - 1) / chunk_size);
-    u32 *offsets = (u32 *)L.bounds;
-    PtrLoad<u32> pl{(const u32 *)cnt};
-    rc = device_exclusive_scan<u32, PtrLoad<u32>>(pl, chunks, offsets, L.scan_ws, st);
-    if (rc) return rc;
-    chunk_decode_u16_kernel<0><<<cdiv(chunks, 4), 128, 0, st>>>(cdf, Lp, in, offsets, n, chunk_size, chunks, sym);
+    chunk_decode_u16_kernel<0><<<cdiv(chunks, 4), 128, 0, as_stream(stream)>>>(cdf, Lp, in, offsets, n, chunk_size, chunks, sym);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }

@@ -282,15 +282,16 @@ int gpc_attr_decode_gaussian(const float *mean, const float *scale, const float 
 
 /* ---- f-3: the chunked GPU coder on the geometry codec's own streams (container version 2; NOT the torchac bitstream: one coder
  * per chunk instead of one per stream).  Encode: lohi as gpc_head_cdf_sym writes it; no host synchronisation.  Decode: one stream
- * at a time (stage i + 1 needs stage i), cdf rows as gpc_head_cdf writes them, workspace of gpc_attr_workspace_bytes. ---- */
+ * at a time (stage i + 1 needs stage i), cdf rows as gpc_head_cdf writes them. ---- */
 size_t gpc_chunk_workspace_bytes(int chunks, int max_chunk);
 /* chunk w = symbols [starts[w], starts[w + 1]) of lohi (device u32[chunks + 1]; at most max_chunk symbols each): the streams of a
  * scene one after the other, every stream cut into chunks of its own length, all coded by ONE launch */
 int gpc_chunk_encode_lohi(const uint32_t *lohi, const uint32_t *starts, int chunks, int max_chunk, int32_t *cnt,
                           uint32_t *offsets, void *ws, size_t ws_bytes, void *stream);
 int gpc_chunk_merge(const void *ws, int chunks, int max_chunk, const uint32_t *offsets, uint8_t *out, void *stream);
-int gpc_chunk_decode_u16(const uint16_t *cdf, const uint8_t *in, const int32_t *cnt, int64_t n, int Lp, int chunk_size,
-                         uint8_t *sym, void *ws, size_t ws_bytes, void *stream);
+/* offsets: device u32[chunks + 1], first byte of every chunk in `in` (prefix sums of the stream's u16 byte counts); Lp <= 32 */
+int gpc_chunk_decode_u16(const uint16_t *cdf, const uint8_t *in, const uint32_t *offsets, int64_t n, int Lp, int chunk_size,
+                         uint8_t *sym, void *stream);
 
 #ifdef __cplusplus
 }
