@@ -227,3 +227,28 @@ def test_lohi_encoder_same_bytes(A):
     ref = O.ac_encode(cdf, sym.astype(np.int16))
     assert out[:ln.value].tobytes() == ref == _enc(lib, cdf, sym)
     assert np.array_equal(_dec(lib, cdf, ref), sym)
+
+
+def test_container_v2_trailer_and_chunk_rule():
+    """Container version 2 (opt-in): the trailing stream that names the format, and the chunk length of a stream --
+    host logic only (the coder itself is GPU code: tests/test_gpu_parity.py::test_container_v2_gpu_chunk_coder)."""
+    from gauspcc_b200 import bitstream
+    from gauspcc_b200.codec import GausPcgcCodec
+    v1 = [b"\x01\x02", b"", b"\xff", b"abc"] * 3
+    assert bitstream.split_v2(v1) == (v1, 0, None)
+    v2 = v1 + [bitstream.v2_trailer(2048, 123456)]
+    st, chunk, n_vox = bitstream.split_v2(v2)
+    assert st == v1 and chunk == 2048 and n_vox == 123456
+    # the outer layout is the reference's: a version-2 file parses with the same reader, one stream more
+    blob = bitstream.write_file(1, np.zeros((2, 3), np.int32), np.array([1, 255], np.uint8), v2)
+    _, bx, bo, back = bitstream.read_file(blob)
+    assert bx.shape == (2, 3) and list(bo) == [1, 255] and back == v2
+    assert bitstream.split_v2(v1 + [b"GPCGC-V2"]) == (v1 + [b"GPCGC-V2"], 0, None)          # a malformed trailer is not a trailer
+    # chunk length of a stream of n symbols: the file's chunk size, at least 64 chunks per stream where 64-symbol chunks allow
+    cl = GausPcgcCodec.chunk_len
+    assert cl(1_000_000, 2048) == 2048 and cl(200_000, 2048) == 2048 and cl(100_000, 2048) == 1563
+    assert cl(9_000, 2048) == 141 and cl(500, 2048) == 64 and cl(10, 2048) == 64 and cl(0, 2048) == 64
+    assert cl(1_000_000, 32) == 32 and cl(5, 1) == 1
+    for n in (1, 63, 64, 65, 4095, 4096, 4097, 131071):
+        c = cl(n, 2048)
+        assert 1 <= c <= 2048 and (n + c - 1) // c <= max(64, (n + 63) // 64 + 1)
