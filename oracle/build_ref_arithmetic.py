@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  The sources stay where they are: the zip is unpacked into a temporary directory, compiled with
 the reference's own flags (setup.py: -O2) for sm_100a, and only the shared object is kept (oracle/_ref/ is git-ignored and
-travels to the GPU box).  tests/test_attr_coder.py and tools/attr_bench.py import it when present to compare the library's
+travels to the GPU box).  tests/test_attr_coder.py and tests/bench_attr_coder.py import it when present to compare the library's
 streams and symbols with the reference kernels' on the same B200; nothing in gauspcc_b200/ ever loads it.
 
     python oracle/build_ref_arithmetic.py [/root/reference]

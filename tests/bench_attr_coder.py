@@ -1,7 +1,8 @@
-"""throughput of the attribute coder on one B200 -- the library's fused Gaussian path and its table path against the
+"""(Lives under tests/ because it loads the reference extension from oracle/_ref: only tests/, smoke() and bench.py may touch oracle/.)
+SURVEY 8f-4: throughput of the attribute coder on one B200 -- the library's fused Gaussian path and its table path against the
 reference extension (oracle/_ref/arithmetic.so, built from the reference's own sources) on the same tensors.
 
-    python tools/attr_bench.py [n_symbols] [reps]       (default 10 000 000 = one file of encoder_gaussian_chunk, 5 reps)
+    python tests/bench_attr_coder.py [n_symbols] [reps]       (default 10 000 000 = one file of encoder_gaussian_chunk, 5 reps)
 
 Prints one JSON line.  Times are CUDA-event times around the calls the reference's encoder_gaussian / decoder_gaussian make
 (calculate_cdf + arithmetic_encode, calculate_cdf + arithmetic_decode); bytes / symbols are checked for identity first."""
