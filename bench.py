@@ -71,16 +71,32 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
+    def _nvml(self):
+        """NVML handle for fast sampling (a query is ~1 ms; an nvidia-smi process is ~0.4 s, one sample per timed region)"""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
+                if nv is not None:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    act = lambda bit: "Active" if r & bit else "Not Active"
+                    self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                         act(0x8), act(0x40), act(0x20), act(0x4)])     # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05 if nv is not None else 0.2)
 
     def summary(self):
         sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
